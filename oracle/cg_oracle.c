@@ -1,0 +1,327 @@
+/* TEST INFRASTRUCTURE ONLY - see cg_oracle.h. Plain-C restatement of the reference's CG path.
+ * Build with -ffp-contract=off: the reference is built with g++ -O2 for baseline x86-64
+ * (solver/CMakeLists.txt:68), i.e. every a*b+c below is a rounded multiply followed by a rounded add.
+ * Every function cites the reference lines it follows (paths relative to /root/reference/). */
+#include "cg_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* solver/grid_system.cpp:8-15 (same in matrix_free_system.cpp:10-16) */
+static double f_rhs(double x, double y) { return 4 * (x * x + y * y) * exp(x * x - y * y); }
+static double u_exact(double x, double y) { return exp(x * x - y * y); }
+
+/* solver/grid_system.cpp:301-318 */
+int cgo_grid_init(cgo_grid* g, int m, int n, double a, double b, double c, double d, int kind) {
+  g->n = n; g->m = m; g->a = a; g->b = b; g->c = c; g->d = d; g->kind = kind;
+  g->hx = (b - a) / (n);
+  g->hy = (d - c) / (m);
+  g->A = -2 * (1 / (g->hx * g->hx) + 1 / (g->hy * g->hy));
+  g->xk = 1 / (g->hx * g->hx);
+  g->yk = 1 / (g->hy * g->hy);
+  if (kind == CGO_LSHAPE) {
+    /* calculate_position_in_upper_area uses n/2 where m/2 is meant and the bottom-block width n/2-1
+     * is only right for even n (grid_system.cpp:103-111): the numbering is self-consistent only for even n == m. */
+    if (n != m || (n % 2) != 0 || n < 4) return -1;
+  } else {
+    if (n < 2 || m < 2) return -1;
+  }
+  return 0;
+}
+
+static double node_x(const cgo_grid* g, int x) { return g->a + x * g->hx; } /* grid_system.cpp:69-72 */
+static double node_y(const cgo_grid* g, int y) { return g->c + y * g->hy; } /* grid_system.cpp:74-77 */
+
+/* solver/grid_system.cpp:17-43 */
+static int is_left_boundary(const cgo_grid* g, int x, int y) {
+  if (g->kind == CGO_RECT) return x == 0;
+  return (x == 0 && (y >= g->m / 2 && y <= g->m)) || (x == g->n / 2 && (y >= 0 && y <= g->m / 2));
+}
+static int is_right_boundary(const cgo_grid* g, int x, int y) { (void)y; return x == g->n; }
+static int is_top_boundary(const cgo_grid* g, int x, int y) { (void)x; return y == g->m; }
+static int is_bottom_boundary(const cgo_grid* g, int x, int y) {
+  if (g->kind == CGO_RECT) return y == 0;
+  return (y == 0 && (x >= g->n / 2 && x <= g->n)) || (y == g->m / 2 && (x >= 0 && x <= g->n / 2));
+}
+
+/* Unknowns = nodes visited by the two loop nests of initiate_matrix (grid_system.cpp:181-185, :227-231). */
+int cgo_is_unknown(const cgo_grid* g, int x, int y) {
+  if (x < 1 || x > g->n - 1 || y < 1 || y > g->m - 1) return 0;
+  if (g->kind == CGO_RECT) return 1;
+  if (y <= g->m / 2) return x > g->n / 2;
+  return 1;
+}
+
+/* solver/grid_system.cpp:84-111 (valid for even n == m, where n/2 == m/2) */
+long cgo_index(const cgo_grid* g, int x, int y) {
+  if (!cgo_is_unknown(g, x, y)) return -1;
+  if (g->kind == CGO_RECT) return (long)(y - 1) * (g->n - 1) + (x - 1);
+  if (y <= g->m / 2) return (long)(g->n / 2 - 1) * (y - 1) + x - g->n / 2 - 1;
+  long upper = (long)(y - g->n / 2 - 1) * (g->n - 1) + x - 1;
+  long bottom = (long)(g->n / 2 - 1) * (g->m / 2 - 1) + (g->n - 1) - g->n / 2 - 1; /* position of (n-1, m/2) */
+  return upper + bottom + 1;
+}
+
+long cgo_size(const cgo_grid* g) {
+  return cgo_index(g, g->n - 1, g->m - 1) + 1; /* grid_system.cpp:162 */
+}
+
+void cgo_node(const cgo_grid* g, long idx, int* x, int* y) {
+  if (g->kind == CGO_RECT) {
+    *y = (int)(idx / (g->n - 1)) + 1;
+    *x = (int)(idx % (g->n - 1)) + 1;
+    return;
+  }
+  long wB = g->n / 2 - 1, NB = wB * (g->m / 2);
+  if (idx < NB) {
+    *y = (int)(idx / wB) + 1;
+    *x = (int)(idx % wB) + g->n / 2 + 1;
+  } else {
+    long k = idx - NB;
+    *y = (int)(k / (g->n - 1)) + g->m / 2 + 1;
+    *x = (int)(k % (g->n - 1)) + 1;
+  }
+}
+
+/* calculate_value, solver/grid_system.cpp:45-67: f minus Dirichlet neighbours in the order left, right, top, bottom */
+static double rhs_value(const cgo_grid* g, int x, int y) {
+  double value = f_rhs(node_x(g, x), node_y(g, y));
+  if (is_left_boundary(g, x - 1, y)) value -= g->xk * u_exact(node_x(g, x - 1), node_y(g, y));
+  if (is_right_boundary(g, x + 1, y)) value -= g->xk * u_exact(node_x(g, x + 1), node_y(g, y));
+  if (is_top_boundary(g, x, y + 1)) value -= g->yk * u_exact(node_x(g, x), node_y(g, y + 1));
+  if (is_bottom_boundary(g, x, y - 1)) value -= g->yk * u_exact(node_x(g, x), node_y(g, y - 1));
+  return value;
+}
+
+/* matrix_free_system.cpp:104-141 / grid_system.cpp:220-221,266-267 */
+void cgo_rhs(const cgo_grid* g, double* b) {
+  long N = cgo_size(g);
+  for (long i = 0; i < N; ++i) {
+    int x, y;
+    cgo_node(g, i, &x, &y);
+    b[i] = rhs_value(g, x, y);
+  }
+}
+
+/* matrix_free_system.cpp:162-199 / grid_system.cpp:276-299 */
+void cgo_true_solution(const cgo_grid* g, double* u) {
+  long N = cgo_size(g);
+  for (long i = 0; i < N; ++i) {
+    int x, y;
+    cgo_node(g, i, &x, &y);
+    u[i] = u_exact(node_x(g, x), node_y(g, y));
+  }
+}
+
+/* grid_system.cpp:188-190, :234-236 */
+void cgo_node_coords(const cgo_grid* g, double* xs, double* ys) {
+  long N = cgo_size(g);
+  for (long i = 0; i < N; ++i) {
+    int x, y;
+    cgo_node(g, i, &x, &y);
+    xs[i] = node_x(g, x);
+    ys[i] = node_y(g, y);
+  }
+}
+
+/* MatrixFreeSystem::apply, matrix_free_system.cpp:203-340. Same accumulation order per row:
+ * y = 0; y += A*x[row]; y += xk*x[left]; y += xk*x[right]; y += yk*x[top]; y += yk*x[bottom];
+ * a neighbour term is dropped when the neighbour is a boundary node (:221,:233,:245,:257). */
+void cgo_apply(const cgo_grid* g, const double* x, double* y) {
+  long N = cgo_size(g);
+  for (long row = 0; row < N; ++row) {
+    int xi, yi;
+    cgo_node(g, row, &xi, &yi);
+    double acc = 0.0;
+    acc += g->A * x[row];
+    if (!is_left_boundary(g, xi - 1, yi)) acc += g->xk * x[cgo_index(g, xi - 1, yi)];
+    if (!is_right_boundary(g, xi + 1, yi)) acc += g->xk * x[cgo_index(g, xi + 1, yi)];
+    if (!is_top_boundary(g, xi, yi + 1)) acc += g->yk * x[cgo_index(g, xi, yi + 1)];
+    if (!is_bottom_boundary(g, xi, yi - 1)) acc += g->yk * x[cgo_index(g, xi, yi - 1)];
+    y[row] = acc;
+  }
+}
+
+/* std::inner_product, sequential (matrix_free_system.cpp:364-366; msg_solver.cpp:224-226) */
+static double dot(long n, const double* a, const double* b) {
+  double s = 0.0;
+  for (long i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+static double max_norm(long n, const double* v) { /* msg_solver.cpp:247-258 */
+  double mx = 0.0;
+  for (long i = 0; i < n; ++i) {
+    double t = fabs(v[i]);
+    if (t > mx) mx = t;
+  }
+  return mx;
+}
+
+/* MatrixFreeSolver::solve, matrix_free_system.cpp:383-482 */
+void cgo_mf_solve(const cgo_grid* g, const double* b, const double* u, double eps, int max_it, double* x,
+                  cgo_mf_info* info, double* hist, int hist_cap, double* snapshot_r, double* snapshot_p) {
+  long n = cgo_size(g);
+  double t0 = now_s();
+  double* r = (double*)malloc(sizeof(double) * n);
+  double* p = (double*)malloc(sizeof(double) * n);
+  double* Ap = (double*)malloc(sizeof(double) * n);
+  double* Ax = (double*)malloc(sizeof(double) * n);
+  double* prev_x = hist ? (double*)malloc(sizeof(double) * n) : NULL;
+  for (long i = 0; i < n; ++i) x[i] = 0.0;                          /* :387 */
+  cgo_apply(g, x, Ax);                                                /* :392 */
+  for (long i = 0; i < n; ++i) r[i] = 1.0 * b[i] + -1.0 * Ax[i];      /* :393 via axpby :374-380 */
+  memcpy(p, r, sizeof(double) * n);                                   /* :396 */
+  double r_norm = sqrt(dot(n, r, r));                                 /* :399 */
+  double initial_r_norm = r_norm;
+  int iterations;
+  for (iterations = 0; iterations < max_it && r_norm > eps * initial_r_norm; ++iterations) { /* :409 */
+    if (prev_x) memcpy(prev_x, x, sizeof(double) * n);               /* :411 */
+    cgo_apply(g, p, Ap);                                              /* :414 */
+    double p_dot_Ap = dot(n, p, Ap);                                  /* :417 */
+    double r_dot_r = dot(n, r, r);                                    /* :418 */
+    double alpha = r_dot_r / p_dot_Ap;                                /* :419 */
+    for (long i = 0; i < n; ++i) x[i] += alpha * p[i];                /* :422 */
+    for (long i = 0; i < n; ++i) r[i] -= alpha * Ap[i];               /* :427 */
+    double new_r_dot_r = dot(n, r, r);                                /* :432 */
+    double beta = new_r_dot_r / r_dot_r;                              /* :433 */
+    for (long i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];           /* :436 */
+    r_norm = sqrt(new_r_dot_r);                                       /* :441 */
+    if (hist && iterations < hist_cap) {                              /* reporting only, :444-468 */
+      double s = 0.0, e = 0.0, rr = 0.0;
+      for (long i = 0; i < n; ++i) { double dlt = x[i] - prev_x[i]; s += dlt * dlt; }
+      for (long i = 0; i < n; ++i) { double dlt = x[i] - u[i]; e += dlt * dlt; }
+      cgo_apply(g, x, Ax);
+      for (long i = 0; i < n; ++i) { double dlt = b[i] - Ax[i]; rr += dlt * dlt; }
+      hist[3 * iterations + 0] = sqrt(s);
+      hist[3 * iterations + 1] = sqrt(rr);
+      hist[3 * iterations + 2] = sqrt(e);
+    }
+  }
+  info->iterations = iterations;
+  info->converged = r_norm <= eps * initial_r_norm;                   /* :472 */
+  info->r0_norm = initial_r_norm;
+  info->r_norm = r_norm;
+  if (snapshot_r) memcpy(snapshot_r, r, sizeof(double) * n);
+  if (snapshot_p) memcpy(snapshot_p, p, sizeof(double) * n);
+  free(r); free(p); free(Ap); free(Ax); free(prev_x);
+  info->seconds = now_s() - t0;
+}
+
+/* Neighbour list of an unknown in the reference's per-row order; returns the count (grid_system.cpp:192-218). */
+static int row_entries(const cgo_grid* g, long row, int* cols, double* vals) {
+  int xi, yi, k = 0;
+  cgo_node(g, row, &xi, &yi);
+  cols[k] = (int)row; vals[k++] = g->A;
+  if (!is_left_boundary(g, xi - 1, yi)) { cols[k] = (int)cgo_index(g, xi - 1, yi); vals[k++] = g->xk; }
+  if (!is_right_boundary(g, xi + 1, yi)) { cols[k] = (int)cgo_index(g, xi + 1, yi); vals[k++] = g->xk; }
+  if (!is_top_boundary(g, xi, yi + 1)) { cols[k] = (int)cgo_index(g, xi, yi + 1); vals[k++] = g->yk; }
+  if (!is_bottom_boundary(g, xi, yi - 1)) { cols[k] = (int)cgo_index(g, xi, yi - 1); vals[k++] = g->yk; }
+  return k;
+}
+
+long cgo_csr_nnz(const cgo_grid* g) {
+  long N = cgo_size(g), nnz = 0;
+  int cols[5];
+  double vals[5];
+  for (long i = 0; i < N; ++i) nnz += row_entries(g, i, cols, vals);
+  return nnz;
+}
+
+/* GridSystem::initiate_matrix + finalize_matrix, grid_system.cpp:122-274 */
+void cgo_csr_assemble(const cgo_grid* g, int* row_map, int* entries, double* values) {
+  long N = cgo_size(g), k = 0;
+  row_map[0] = 0;
+  for (long i = 0; i < N; ++i) {
+    k += row_entries(g, i, entries + k, values + k);
+    row_map[i + 1] = (int)k;
+  }
+}
+
+/* KokkosSparse::spmv("N", 1.0, A, x, 0.0, y) as restated in oracle/shim/KokkosSparse_spmv.hpp */
+void cgo_spmv(long nrows, const int* row_map, const int* entries, const double* values, const double* x,
+              double* y) {
+  for (long i = 0; i < nrows; ++i) {
+    double sum = 0.0;
+    for (int k = row_map[i]; k < row_map[i + 1]; ++k) sum += values[k] * x[entries[k]];
+    y[i] = 1.0 * sum;
+  }
+}
+
+/* MSGSolver::solve, msg_solver.cpp:10-212 */
+void cgo_msg_solve(long nrows, const int* row_map, const int* entries, const double* values, const double* b,
+                   const double* u, double eps_p, double eps_r, double eps_e, int max_it, double* x,
+                   cgo_msg_info* info, double* cb_log, int cb_cap) {
+  long n = nrows;
+  double t0 = now_s();
+  double* x_prev = (double*)malloc(sizeof(double) * n);
+  double* r = (double*)malloc(sizeof(double) * n);
+  double* z = (double*)malloc(sizeof(double) * n);
+  double* A_z = (double*)malloc(sizeof(double) * n);
+  double* tmp = (double*)malloc(sizeof(double) * n);
+  int ncb = 0;
+  for (long i = 0; i < n; ++i) x[i] = 0.0;                 /* :33 */
+  memcpy(r, b, sizeof(double) * n);                        /* :36 */
+  memcpy(z, r, sizeof(double) * n);                        /* :39 */
+  double r_norm = sqrt(dot(n, r, r));                      /* :42 */
+  double r_max_norm = max_norm(n, r);                      /* :43 */
+  int iterationsDone = 0, converged = 0, stop_reason = CGO_STOP_ITERATIONS;
+  double precision_max_norm = DBL_MAX, error_max_norm = DBL_MAX; /* :56-61 */
+  if (u) {                                                 /* :64-72 */
+    for (long i = 0; i < n; ++i) tmp[i] = x[i] - u[i];
+    error_max_norm = max_norm(n, tmp);
+  }
+#define CGO_CB(it)                                                                   \
+  do {                                                                               \
+    if (cb_log && ncb < cb_cap) {                                                    \
+      cb_log[4 * ncb + 0] = (double)(it); cb_log[4 * ncb + 1] = precision_max_norm;  \
+      cb_log[4 * ncb + 2] = r_max_norm;   cb_log[4 * ncb + 3] = error_max_norm;      \
+    }                                                                                \
+    ++ncb;                                                                           \
+  } while (0)
+  CGO_CB(0);                                               /* :75-77 */
+  while (iterationsDone < max_it) {                        /* :80 */
+    memcpy(x_prev, x, sizeof(double) * n);                 /* :90 */
+    cgo_spmv(n, row_map, entries, values, z, A_z);         /* :93 */
+    double rz = dot(n, r, z);                              /* :96 */
+    double Az_z = dot(n, A_z, z);                          /* :99 */
+    double alpha = rz / Az_z;                              /* :102 */
+    for (long i = 0; i < n; ++i) x[i] = x[i] + alpha * z[i];   /* :105-107 */
+    for (long i = 0; i < n; ++i) r[i] = r[i] - alpha * A_z[i]; /* :110-112 */
+    iterationsDone++;                                      /* :115 */
+    r_norm = sqrt(dot(n, r, r));                           /* :120 */
+    r_max_norm = max_norm(n, r);                           /* :121 */
+    for (long i = 0; i < n; ++i) tmp[i] = x[i] - x_prev[i];    /* :124-127 */
+    precision_max_norm = max_norm(n, tmp);                 /* :129 */
+    if (u) {                                               /* :132-139 */
+      for (long i = 0; i < n; ++i) tmp[i] = x[i] - u[i];
+      error_max_norm = max_norm(n, tmp);
+    }
+    if (eps_p > 0 && precision_max_norm < eps_p) { converged = 1; stop_reason = CGO_STOP_PRECISION; break; }   /* :144 */
+    if (eps_r > 0 && r_max_norm < eps_r) { converged = 1; stop_reason = CGO_STOP_RESIDUAL; break; }            /* :151 */
+    if (eps_e > 0 && u && error_max_norm < eps_e) { converged = 1; stop_reason = CGO_STOP_EXACT_ERROR; break; } /* :158 */
+    double beta = (r_norm * r_norm) / (rz);                /* :165 */
+    for (long i = 0; i < n; ++i) z[i] = r[i] + beta * z[i];    /* :167-169 */
+    if (iterationsDone % 100 == 0 || iterationsDone == 1) CGO_CB(iterationsDone); /* :172-183 */
+  }
+  CGO_CB(iterationsDone);                                  /* :193-195 */
+#undef CGO_CB
+  info->iterations = iterationsDone;
+  info->converged = converged;
+  info->stop_reason = stop_reason;
+  info->r_max = r_max_norm;
+  info->dx_max = precision_max_norm;
+  info->err_max = error_max_norm;
+  info->r_l2 = r_norm;
+  info->n_callbacks = ncb;
+  free(x_prev); free(r); free(z); free(A_z); free(tmp);
+  info->seconds = now_s() - t0;
+}
