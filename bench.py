@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py - CG GDOF-iter/s of the matrix-free Dirichlet-Poisson solve (BASELINE.json metric).
+
+A "step" is one fixed-iteration solve (default 500 CG iterations) of the L-shaped
+Dirichlet system on an n x n grid through the C ABI (b200cg_solve), i.e. what MatrixFreeSolver::solve does.
+  value : whole-job DOF-iterations/s with the right-hand side already resident in HBM and the solution left
+          there; timed on the device (CUDA events of the library's solve stream), max over ranks.
+  e2e   : the same solve with HOST buffers (pinned): H2D of b and D2H of x inside the timed region.
+N > 1 (torchrun, one process per GPU): row slabs of one larger grid, n_G = even(round(n * sqrt(G))), so the
+unknowns per GPU stay fixed (weak scaling); halo rows and scalar reductions go over NCCL inside the library.
+
+--impl reference times the reference's own CPU solver (unmodified sources compiled into oracle/_ref, else the
+C port in oracle/) on a bounded sample of the same workload, on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cg_gdof_iter_per_s"
+UNIT = "GDOF-iter/s"
+BYTES_MODEL = 80.0        # algorithmic bytes per DOF-iteration of the store-Ap formulation
+BYTES_UPD = 48.0          # update-phase kernel: r, p_old, x in; x, r, p out
+BYTES_DOT = 16.0          # dot-phase kernel: r, p_old in
+NOMINAL_HBM_GBS = 8000.0  # BASELINE.json "vs 8 TB/s peak"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=16384, help="grid intervals per side at 1 GPU")
+    ap.add_argument("--iters", type=int, default=500, help="CG iterations per step")
+    ap.add_argument("--domain", default="lshape", choices=["lshape", "rect"])
+    ap.add_argument("--op", default="mf", choices=["mf", "csr"])
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--iters-per-graph", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-n", type=int, default=4096)
+    ap.add_argument("--cpu-sample-iters", type=int, default=5)
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        return json.load(open(path)).get("upd_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc = None
+        self.path = None
+        self.idx = device_index
+        if shutil.which("nvidia-smi"):
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(device_index)], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def grid_side(n1, gpus, domain):
+    if gpus == 1:
+        return n1
+    n = int(round(n1 * math.sqrt(gpus)))
+    if domain == "lshape" and n % 2:
+        n += 1
+    return n
+
+
+def workload_name(n, iters, domain, op):
+    return (f"{n}x{n} grid, {'L-shaped (reference) domain' if domain == 'lshape' else 'full rectangle'}, "
+            f"{'matrix-free' if op == 'mf' else 'assembled CSR'} CG fp64, fixed {iters} iterations per solve, unit square")
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def time_reference(n, iters):
+    """One bounded sample of the workload on the host: MatrixFreeSolver::solve for `iters` iterations."""
+    from oracle import oracle
+
+    if oracle.Reference.available():
+        mf = oracle.Reference.MatrixFree(n, n, 0.0, 1.0, 0.0, 1.0)
+        s = mf.solve(eps=0.0, max_it=iters)
+        return mf.N, s["iterations"], s["seconds"], "reference"
+    o = oracle.Oracle(n, n, 0.0, 1.0, 0.0, 1.0)
+    b = o.rhs()
+    s = o.mf_solve(b=b, eps=0.0, max_it=iters, with_hist=True)  # with_hist: the reference's per-iteration reporting work
+    return o.N, s["iterations"], s["seconds"], "port"
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    n, iters = min(args.cpu_sample_n, 2048), 3
+    for _ in range(args.warmup):
+        time_reference(n, iters)
+    secs, dofit = 0.0, 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        N, its, s, kind = time_reference(n, iters)
+        secs += s
+        dofit += N * its
+    value = dofit / secs / 1e9
+    sample = (f"MatrixFreeSolver::solve on the {n}x{n} L-shaped grid ({N} unknowns), {iters} iterations per step "
+              f"(same operator, rhs and x0 as the {args.n}^2 workload; the reference code is serial)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(grid_side(args.n, args.gpus, args.domain), args.iters, args.domain, args.op),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch  # plumbing only: process group, barrier, max-over-ranks
+
+    from iterative_solvers_b200 import capi
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    capi.lib()
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - libb200cg has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm_id = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        blob = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            blob = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(blob, src=0)
+        comm_id = bytes(blob.cpu().tolist())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = grid_side(args.n, world, args.domain)
+    domain = capi.DOMAIN_LSHAPE if args.domain == "lshape" else capi.DOMAIN_RECT
+    op = capi.OP_MATRIX_FREE if args.op == "mf" else capi.OP_CSR
+    plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local_rank, rank=rank, world=world,
+                     comm_id=comm_id, tile_rows=args.tile_rows)
+    plan.build_rhs()  # synthetic, deterministic: the reference's analytic f and Dirichlet data
+    if op == capi.OP_CSR:
+        plan.assemble_csr()
+    n_local = plan.n_local
+    solve_kw = dict(op=op, rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=args.iters, iters_per_graph=args.iters_per_graph)
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        plan.solve(rhs_on_device=True, keep_x_on_device=True, **solve_kw)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, dot_ms, upd_ms, samples, its_done = 0.0, 0, 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        _, info = plan.solve(rhs_on_device=True, keep_x_on_device=True, **solve_kw)
+        dev_ms += info["device_ms"]
+        launches += info["kernel_launches"]
+        its_done += info["iterations"]
+        if info["kernel_samples"]:
+            dot_ms += info["dot_kernel_ms"]
+            upd_ms += info["upd_kernel_ms"]
+            samples += 1
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    total_dofit = float(plan.N) * its_done  # all ranks run the same iteration count
+    value = total_dofit / (dev_ms * 1e-3) / 1e9
+    launches_all = int(sum_over_ranks(float(launches)))
+
+    # ---- e2e: host buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        hb = capi.PinnedArray(n_local)
+        hx = capi.PinnedArray(n_local)
+        hb.array[:] = plan.get_rhs()
+        for _ in range(max(1, min(args.warmup, 2))):
+            plan.solve(b=hb.array, x_out=hx.array, **solve_kw)
+        barrier()
+        t0 = time.perf_counter()
+        e_its, e_dev = 0, 0.0
+        for _ in range(args.steps):
+            _, info = plan.solve(b=hb.array, x_out=hx.array, **solve_kw)
+            e_its += info["iterations"]
+            e_dev += info["device_ms"]
+            checksum = float(hx.array[0] + hx.array[-1])  # the D2H result is read on the host every step
+        barrier()
+        e_wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e = {"value": float(plan.N) * e_its / (e_wall * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(sum_over_ranks(float(n_local * 8))),
+               "d2h_bytes_per_step": int(sum_over_ranks(float(n_local * 8))),
+               "ms_per_step": e_wall / max(args.steps, 1), "device_ms_per_step": max_over_ranks(e_dev) / max(args.steps, 1),
+               "timing": "host wall clock around the C-ABI calls, barrier + device synchronize on both sides",
+               "checksum": checksum}
+        hb.free()
+        hx.free()
+
+    if rank != 0:
+        plan.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    roofline = None
+    if samples and op == capi.OP_MATRIX_FREE:
+        upd_s = (upd_ms / samples) * 1e-3
+        dot_s = (dot_ms / samples) * 1e-3
+        achieved = BYTES_UPD * n_local / upd_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "cg_tile_kernel<MODE_UPD> (update phase)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_UPD * n_local,
+                    "avg_launch_ms": upd_s * 1e3, "launches_sampled": samples,
+                    "dot_kernel": {"achieved": BYTES_DOT * n_local / dot_s / 1e9 if dot_s > 0 else None,
+                                   "avg_launch_ms": dot_s * 1e3, "algorithmic_bytes_per_launch": BYTES_DOT * n_local},
+                    "kernel_share_of_step": (upd_s + dot_s) * 1e3 * (its_done / max(args.steps, 1)) /
+                                            (dev_ms / max(args.steps, 1))}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        N, its, secs, kind = time_reference(args.cpu_sample_n, args.cpu_sample_iters)
+        cpu_baseline = {"value": N * its / secs / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                        "host_cores": os.cpu_count(), "seconds": secs,
+                        "sample": (f"MatrixFreeSolver::solve, {args.cpu_sample_n}^2 L-shaped grid ({N} unknowns), "
+                                   f"{its} iterations, 1 core (the reference code is serial)")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, args.iters, args.domain, args.op), "grid_n": n, "unknowns": plan.N,
+                   "unknowns_per_gpu": plan.N / world, "iterations_per_step": args.iters,
+                   "parallelism": f"row-slab x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs_exceed_l2" if n_local * 8 > 200e6 else "inputs_fit_l2_no_flush",
+                   "timing": "CUDA events on the library's solve stream, summed over steps, max over ranks",
+                   "wall_ms_per_step": wall_ms / max(args.steps, 1)},
+        "hbm_gbs_at_80B_per_dof_iter": value * BYTES_MODEL / world,
+        "frac_of_8tbs_per_gpu": value * BYTES_MODEL / world / NOMINAL_HBM_GBS,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

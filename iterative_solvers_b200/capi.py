@@ -1,0 +1,278 @@
+"""ctypes mirror of include/b200cg.h. Thin by design: argument marshalling and status -> exception only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libb200cg.so")
+
+DOMAIN_LSHAPE, DOMAIN_RECT = 0, 1
+OP_MATRIX_FREE, OP_CSR = 0, 1
+RULE_REL_L2, RULE_MAXNORM = 0, 1
+STOP_NAMES = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]
+ERR_NO_DEVICE = 2
+
+# every symbol include/b200cg.h declares (tests/test_abi.py checks the two lists against each other)
+EXPORTS = [
+    "b200cg_last_error", "b200cg_version", "b200cg_device_count", "b200cg_alloc_pinned", "b200cg_free_pinned",
+    "b200cg_comm_unique_id", "b200cg_plan_create", "b200cg_plan_destroy", "b200cg_size", "b200cg_local_range",
+    "b200cg_partition",
+    "b200cg_build_rhs", "b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_coords",
+    "b200cg_apply", "b200cg_set_csr", "b200cg_assemble_csr", "b200cg_get_csr", "b200cg_csr_apply",
+    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution",
+]
+
+
+class B200CGError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"b200cg status {status}: {message}")
+        self.status = status
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
+                ("d", C.c_double), ("domain", C.c_int), ("device", C.c_int), ("rank", C.c_int),
+                ("world", C.c_int), ("comm_id", C.c_void_p), ("tile_rows", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class Params(C.Structure):
+    _fields_ = [("op", C.c_int), ("rule", C.c_int), ("eps_rel", C.c_double), ("eps_p", C.c_double),
+                ("eps_r", C.c_double), ("eps_e", C.c_double), ("max_it", C.c_int), ("callback_every", C.c_int),
+                ("rhs_on_device", C.c_int), ("keep_x_on_device", C.c_int), ("iters_per_graph", C.c_int),
+                ("reserved", C.c_int * 7)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("stop_reason", C.c_int),
+                ("r0_l2", C.c_double), ("r_l2", C.c_double), ("r_max", C.c_double), ("dx_max", C.c_double),
+                ("err_max", C.c_double), ("total_ms", C.c_double), ("solve_ms", C.c_double), ("device_ms", C.c_double),
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("dot_kernel_ms", C.c_double),
+                ("upd_kernel_ms", C.c_double), ("kernel_samples", C.c_int), ("local_unknowns", C.c_int64),
+                ("reserved", C.c_int * 6)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["stop_reason"] = STOP_NAMES[self.stop_reason]
+        d["converged"] = bool(self.converged)
+        return d
+
+
+ITER_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double)
+
+_lib = None
+
+
+def lib():
+    """Loads libb200cg.so. Raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200CGError(-1, f"{LIB_PATH} is missing: run `python -m iterative_solvers_b200.build` "
+                                  "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.b200cg_last_error.restype = C.c_char_p
+        L.b200cg_plan_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(PlanDesc)]
+        L.b200cg_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(SolveInfo), C.c_void_p, C.c_void_p, C.c_void_p]
+        for name in ("b200cg_plan_destroy", "b200cg_build_rhs"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        for name in ("b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_solution"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("b200cg_get_coords", "b200cg_apply", "b200cg_csr_apply"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200cg_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.b200cg_local_range.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.b200cg_set_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200cg_assemble_csr.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.b200cg_get_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200cg_postprocess.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b200cg_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.b200cg_free_pinned.argtypes = [C.c_void_p]
+        L.b200cg_comm_unique_id.argtypes = [C.c_void_p]
+        L.b200cg_device_count.argtypes = [C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise B200CGError(status, lib().b200cg_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    status = lib().b200cg_device_count(C.byref(n))
+    return n.value if status == 0 else 0
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().b200cg_comm_unique_id(buf))
+    return buf.raw
+
+
+def partition(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1):
+    """Row slab of `rank` among `world`: (y_lo, y_hi, lo, hi, N). Pure geometry - works without a GPU."""
+    desc = PlanDesc(n=int(n), m=int(m), a=0.0, b=1.0, c=0.0, d=1.0, domain=int(domain), device=0, rank=int(rank),
+                    world=int(world))
+    ylo, yhi, lo, hi, N = C.c_int(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+    check(lib().b200cg_partition(C.byref(desc), C.byref(ylo), C.byref(yhi), C.byref(lo), C.byref(hi), C.byref(N)))
+    return ylo.value, yhi.value, lo.value, hi.value, N.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """fp64 host array in page-locked memory (b200cg_alloc_pinned) exposed as a numpy view."""
+
+    def __init__(self, n):
+        self.ptr = C.c_void_p()
+        check(lib().b200cg_alloc_pinned(C.byref(self.ptr), C.c_size_t(max(int(n), 1) * 8)))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_double)), shape=(int(n),))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().b200cg_free_pinned(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Plan:
+    """b200cg_plan_t. Constructor arguments follow GridSystem / MatrixFreeSystem: (m, n, a, b, c, d)."""
+
+    def __init__(self, m, n, a=0.0, b=1.0, c=0.0, d=1.0, domain=DOMAIN_LSHAPE, device=0, rank=0, world=1,
+                 comm_id: bytes | None = None, tile_rows=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self._id = C.create_string_buffer(comm_id, 128) if comm_id else None
+        desc = PlanDesc(n=int(n), m=int(m), a=a, b=b, c=c, d=d, domain=int(domain), device=int(device),
+                        rank=int(rank), world=int(world),
+                        comm_id=C.cast(self._id, C.c_void_p) if self._id else None, tile_rows=int(tile_rows))
+        check(self.L.b200cg_plan_create(C.byref(self.h), C.byref(desc)))
+        nn = C.c_int64()
+        check(self.L.b200cg_size(self.h, C.byref(nn)))
+        self.N = nn.value
+        lo, hi = C.c_int64(), C.c_int64()
+        check(self.L.b200cg_local_range(self.h, C.byref(lo), C.byref(hi)))
+        self.lo, self.hi = lo.value, hi.value
+        self.n_local = self.hi - self.lo
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200cg_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- setup data
+    def build_rhs(self):
+        check(self.L.b200cg_build_rhs(self.h))
+
+    def set_rhs(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert b.shape == (self.n_local,)
+        check(self.L.b200cg_set_rhs(self.h, _ptr(b)))
+
+    def _out(self, fn):
+        out = np.empty(self.n_local)
+        check(fn(self.h, _ptr(out)))
+        return out
+
+    def get_rhs(self):
+        return self._out(self.L.b200cg_get_rhs)
+
+    def true_solution(self):
+        return self._out(self.L.b200cg_get_true_solution)
+
+    def get_solution(self):
+        return self._out(self.L.b200cg_get_solution)
+
+    def coords(self):
+        xs, ys = np.empty(self.n_local), np.empty(self.n_local)
+        check(self.L.b200cg_get_coords(self.h, _ptr(xs), _ptr(ys)))
+        return xs, ys
+
+    # ---- operator
+    def apply(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.n_local,)
+        y = np.empty(self.n_local)
+        check(self.L.b200cg_apply(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def set_csr(self, row_map, entries, values):
+        row_map = np.ascontiguousarray(row_map, dtype=np.int32)
+        entries = np.ascontiguousarray(entries, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        check(self.L.b200cg_set_csr(self.h, len(row_map) - 1, len(values), _ptr(row_map), _ptr(entries),
+                                    _ptr(values)))
+
+    def assemble_csr(self):
+        nnz = C.c_int64()
+        check(self.L.b200cg_assemble_csr(self.h, C.byref(nnz)))
+        return nnz.value
+
+    def get_csr(self, nnz):
+        row_map = np.empty(self.N + 1, dtype=np.int32)
+        entries = np.empty(nnz, dtype=np.int32)
+        values = np.empty(nnz)
+        check(self.L.b200cg_get_csr(self.h, _ptr(row_map), _ptr(entries), _ptr(values)))
+        return row_map, entries, values
+
+    def csr_apply(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.N)
+        check(self.L.b200cg_csr_apply(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    # ---- solve
+    def solve(self, b=None, u=None, x_out=None, op=OP_MATRIX_FREE, rule=RULE_REL_L2, eps_rel=1e-6, eps_p=-1.0,
+              eps_r=-1.0, eps_e=-1.0, max_it=10000, callback=None, callback_every=100, rhs_on_device=False,
+              keep_x_on_device=False, iters_per_graph=0, stop_flag=None):
+        """Returns (x, info dict). b / u / x_out may be numpy arrays or PinnedArray.array views."""
+        prm = Params(op=op, rule=rule, eps_rel=eps_rel, eps_p=eps_p, eps_r=eps_r, eps_e=eps_e, max_it=int(max_it),
+                     callback_every=int(callback_every), rhs_on_device=int(bool(rhs_on_device)),
+                     keep_x_on_device=int(bool(keep_x_on_device)), iters_per_graph=int(iters_per_graph))
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float64)
+            assert b.shape == (self.n_local,)
+        if u is not None:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+        if x_out is None and not keep_x_on_device:
+            x_out = np.empty(self.n_local)
+        info = SolveInfo()
+        cb = None
+        if callback is not None:
+            cb = ITER_CB(lambda _user, it, p, r, e: callback(it, p, r, e))
+        flag_ptr = None if stop_flag is None else C.cast(C.byref(stop_flag), C.c_void_p)
+        check(self.L.b200cg_solve(self.h, C.byref(prm), _ptr(b), _ptr(u), _ptr(x_out), C.byref(info),
+                                  C.cast(cb, C.c_void_p) if cb else None, None, flag_ptr))
+        return x_out, info.as_dict()
+
+    def postprocess(self, op=OP_MATRIX_FREE, want_residual=True, want_error=True):
+        res = np.empty(self.n_local) if want_residual else None
+        err = np.empty(self.n_local) if want_error else None
+        check(self.L.b200cg_postprocess(self.h, int(op), _ptr(res), _ptr(err)))
+        return res, err

@@ -1,0 +1,848 @@
+// libb200cg: C ABI (include/b200cg.h) over the sm_100a kernels in kernels.cuh / csr_kernels.cuh.
+// Host side: plan (geometry + device buffers), CUDA-graph captured CG loop with device-resident scalars.
+// No CPU fallback: every compute entry point fails loudly without a CUDA device.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200cg.h"
+#include "kernels.cuh"
+#include "csr_kernels.cuh"
+#include "comm.h"
+
+using namespace b200cg;
+
+// ------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? B200CG_ERR_NO_DEVICE \
+                                                                                 : B200CG_ERR_CUDA, \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+  } while (0)
+
+#define RET(call)                       \
+  do {                                  \
+    int rc__ = (call);                  \
+    if (rc__ != B200CG_OK) return rc__; \
+  } while (0)
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------- plan
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int iters = 0;
+  int kernels = 0;
+};
+
+struct b200cg_plan_s {
+  b200cg_plan_desc desc;
+  Geom g;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  size_t vec_elems = 0;  // doubles per pitched vector
+  double* r[2] = {nullptr, nullptr};
+  double* p[2] = {nullptr, nullptr};
+  double* x = nullptr;
+  double* b = nullptr;
+  double* u = nullptr;
+  double* va = nullptr;  // scratch vectors for apply / postprocess (lazy)
+  double* vb = nullptr;
+  double* compact = nullptr;  // staging buffer in the reference's compact ordering (local range)
+  DevState* d_state = nullptr;
+  DevState* h_state = nullptr;  // pinned mirror
+  CbRecord* d_log = nullptr;
+  CbRecord* h_log = nullptr;  // pinned mirror
+  double* d_partials = nullptr;
+  int partial_slots = 0;
+  cudaEvent_t ev[8] = {};
+  bool have_rhs = false, have_u = false, have_solution = false;
+  std::map<int, GraphEntry> graphs;
+  CsrData csr;
+  Comm comm;
+  int64_t n_global = 0;
+  std::vector<int> ycuts;  // row cuts of all ranks
+};
+
+static long long row_start(const Geom& g, int y) {  // compact index of the first unknown of row y
+  if (g.ysplit && y <= g.ysplit) return (long long)(y - 1) * g.wB;
+  return g.NB + (long long)(y - g.ysplit - 1) * g.wU;
+}
+
+static int setup_geometry(b200cg_plan_s* P) {
+  const b200cg_plan_desc& d = P->desc;
+  Geom& g = P->g;
+  memset(&g, 0, sizeof(g));
+  if (d.domain == B200CG_DOMAIN_LSHAPE) {
+    if (d.n != d.m || (d.n % 2) != 0 || d.n < 4)
+      return fail(B200CG_ERR_INVALID_ARG,
+                  "L-shaped domain needs even n == m >= 4 (got n=%d, m=%d): the reference numbering "
+                  "(grid_system.cpp:103-111) is only self-consistent there",
+                  d.n, d.m);
+  } else if (d.domain == B200CG_DOMAIN_RECT) {
+    if (d.n < 2 || d.m < 2) return fail(B200CG_ERR_INVALID_ARG, "RECT domain needs n, m >= 2");
+  } else {
+    return fail(B200CG_ERR_INVALID_ARG, "unknown domain kind %d", d.domain);
+  }
+  if (!(d.b > d.a) || !(d.d > d.c)) return fail(B200CG_ERR_INVALID_ARG, "empty domain [a,b]x[c,d]");
+  g.n = d.n;
+  g.m = d.m;
+  g.a = d.a;
+  g.c = d.c;
+  g.hx = (d.b - d.a) / (d.n);  // grid_system.cpp:314-318
+  g.hy = (d.d - d.c) / (d.m);
+  g.A = -2 * (1 / (g.hx * g.hx) + 1 / (g.hy * g.hy));
+  g.xk = 1 / (g.hx * g.hx);
+  g.yk = 1 / (g.hy * g.hy);
+  if (d.domain == B200CG_DOMAIN_LSHAPE) {
+    g.xsplit = d.n / 2;
+    g.ysplit = d.m / 2;
+    g.wB = d.n / 2 - 1;
+    g.wU = d.n - 1;
+    g.NB = (long long)g.wB * (d.m / 2);
+  } else {
+    g.xsplit = 0;
+    g.ysplit = 0;
+    g.wB = 0;
+    g.wU = d.n - 1;
+    g.NB = 0;
+  }
+  P->n_global = row_start(g, d.m - 1) + g.wU;
+
+  // row slabs balanced by unknowns (block B rows are narrower than block U rows)
+  const int world = d.world > 1 ? d.world : 1;
+  const int rank = d.world > 1 ? d.rank : 0;
+  if (rank < 0 || rank >= world) return fail(B200CG_ERR_INVALID_ARG, "rank %d outside world %d", rank, world);
+  if (world > d.m - 1) return fail(B200CG_ERR_INVALID_ARG, "more ranks (%d) than unknown rows (%d)", world, d.m - 1);
+  P->ycuts.assign(world + 1, 1);
+  {
+    int y = 1;
+    for (int k = 1; k < world; ++k) {
+      const long long target = (long long)((double)P->n_global * k / world);
+      while (y < d.m - 1 && row_start(g, y + 1) <= target) ++y;
+      // keep at least one row per rank
+      y = std::max(y, P->ycuts[k - 1] + 1);
+      y = std::min(y, d.m - 1 - (world - k) + 1);
+      P->ycuts[k] = y;
+    }
+    P->ycuts[world] = d.m;
+  }
+  g.ylo = P->ycuts[rank];
+  g.yhi = P->ycuts[rank + 1];
+  g.ybase = g.ylo - 1;
+  g.yrows = g.yhi - g.ylo + 2;
+  g.lo = row_start(g, g.ylo);
+  g.hi = (g.yhi >= d.m) ? P->n_global : row_start(g, g.yhi);
+  g.pitch = ((d.n + 1 + XOFF) + 15) / 16 * 16;
+
+  g.tile_rows = d.tile_rows > 0 ? d.tile_rows : 32;
+  g.strips = (d.n - 1) / STRIP_OUT + 1;
+  g.stripB0 = (g.xsplit + 1) / STRIP_OUT;
+  g.yB0 = g.ylo;
+  g.yB1 = std::max(g.ylo, std::min(g.yhi, g.ysplit + 1));
+  g.yU0 = std::max(g.ylo, g.ysplit + 1);
+  g.yU1 = std::max(g.yU0, g.yhi);
+  if (g.ysplit == 0) g.yB1 = g.yB0;
+  g.chunksB = (g.yB1 - g.yB0 + g.tile_rows - 1) / g.tile_rows;
+  g.chunksU = (g.yU1 - g.yU0 + g.tile_rows - 1) / g.tile_rows;
+  g.tilesB = g.chunksB * (g.strips - g.stripB0);
+  g.tiles = g.tilesB + g.chunksU * g.strips;
+  return B200CG_OK;
+}
+
+static int ew_grid(const b200cg_plan_s* P, long long work_items) {
+  long long blocks = (work_items + CTA_THREADS - 1) / CTA_THREADS;
+  long long cap = (long long)P->sms * 16;
+  return (int)std::max(1LL, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------------------------------- library
+extern "C" const char* b200cg_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b200cg_version(void) { return B200CG_VERSION; }
+
+extern "C" int b200cg_device_count(int* count) {
+  if (!count) return fail(B200CG_ERR_INVALID_ARG, "count is NULL");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+    return fail(B200CG_ERR_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(e));
+  }
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_alloc_pinned(void** ptr, size_t bytes) {
+  if (!ptr) return fail(B200CG_ERR_INVALID_ARG, "ptr is NULL");
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return B200CG_OK;
+}
+extern "C" int b200cg_free_pinned(void* ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_comm_unique_id(void* id128) {
+  if (!id128) return fail(B200CG_ERR_INVALID_ARG, "id128 is NULL");
+  std::string err;
+  if (!comm_unique_id(id128, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  return B200CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- plan API
+static void free_plan(b200cg_plan_s* P) {
+  if (!P) return;
+  cudaSetDevice(P->desc.device);
+  for (auto& kv : P->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  comm_destroy(&P->comm);
+  csr_free(&P->csr);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(P->r[i]);
+    cudaFree(P->p[i]);
+  }
+  cudaFree(P->x);
+  cudaFree(P->b);
+  cudaFree(P->u);
+  cudaFree(P->va);
+  cudaFree(P->vb);
+  cudaFree(P->compact);
+  cudaFree(P->d_state);
+  cudaFree(P->d_log);
+  cudaFree(P->d_partials);
+  if (P->h_state) cudaFreeHost(P->h_state);
+  if (P->h_log) cudaFreeHost(P->h_log);
+  for (auto& e : P->ev)
+    if (e) cudaEventDestroy(e);
+  if (P->stream) cudaStreamDestroy(P->stream);
+  delete P;
+}
+
+static int alloc_vec(b200cg_plan_s* P, double** v) {
+  CU(cudaMalloc(v, P->vec_elems * sizeof(double)));
+  CU(cudaMemsetAsync(*v, 0, P->vec_elems * sizeof(double), P->stream));
+  return B200CG_OK;
+}
+
+static int plan_create_impl(b200cg_plan_s* P) {
+  int ndev = 0;
+  RET(b200cg_device_count(&ndev));
+  if (ndev <= 0) return fail(B200CG_ERR_NO_DEVICE, "no CUDA device visible: libb200cg has no CPU fallback");
+  if (P->desc.device < 0 || P->desc.device >= ndev)
+    return fail(B200CG_ERR_INVALID_ARG, "device %d outside [0, %d)", P->desc.device, ndev);
+  RET(setup_geometry(P));
+  CU(cudaSetDevice(P->desc.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, P->desc.device));
+  if (prop.major < 10)
+    return fail(B200CG_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
+                prop.major, prop.minor);
+  P->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+  for (auto& e : P->ev) CU(cudaEventCreate(&e));
+  const Geom& g = P->g;
+  P->vec_elems = (size_t)g.yrows * (size_t)g.pitch;
+  for (int i = 0; i < 2; ++i) {
+    RET(alloc_vec(P, &P->r[i]));
+    RET(alloc_vec(P, &P->p[i]));
+  }
+  RET(alloc_vec(P, &P->x));
+  RET(alloc_vec(P, &P->b));
+  CU(cudaMalloc(&P->compact, std::max<long long>(g.hi - g.lo, 1) * sizeof(double)));
+  CU(cudaMalloc(&P->d_state, sizeof(DevState)));
+  CU(cudaMemsetAsync(P->d_state, 0, sizeof(DevState), P->stream));
+  CU(cudaHostAlloc(&P->h_state, sizeof(DevState), cudaHostAllocDefault));
+  memset(P->h_state, 0, sizeof(DevState));
+  CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
+  CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
+  P->partial_slots = std::max(g.tiles, P->sms * 16) + 64;
+  CU(cudaMalloc(&P->d_partials, sizeof(double) * MAX_PARTIALS * (size_t)P->partial_slots));
+  if (P->desc.world > 1) {
+    std::string err;
+    if (!P->desc.comm_id) return fail(B200CG_ERR_INVALID_ARG, "world > 1 needs comm_id (b200cg_comm_unique_id)");
+    if (!comm_init(&P->comm, P->desc.comm_id, P->desc.rank, P->desc.world, P->stream, &err))
+      return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  }
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_plan_create(b200cg_plan_t* plan, const b200cg_plan_desc* desc) {
+  if (!plan || !desc) return fail(B200CG_ERR_INVALID_ARG, "plan/desc is NULL");
+  *plan = nullptr;
+  b200cg_plan_s* P = new b200cg_plan_s();
+  P->desc = *desc;
+  int rc = plan_create_impl(P);
+  if (rc != B200CG_OK) {
+    std::string keep = g_last_error;
+    free_plan(P);
+    cudaGetLastError();
+    g_last_error = keep;
+    return rc;
+  }
+  *plan = P;
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_plan_destroy(b200cg_plan_t plan) {
+  free_plan(plan);
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_size(b200cg_plan_t P, int64_t* n) {
+  if (!P || !n) return fail(B200CG_ERR_INVALID_ARG, "plan/n is NULL");
+  *n = P->n_global;
+  return B200CG_OK;
+}
+extern "C" int b200cg_local_range(b200cg_plan_t P, int64_t* lo, int64_t* hi) {
+  if (!P || !lo || !hi) return fail(B200CG_ERR_INVALID_ARG, "plan/lo/hi is NULL");
+  *lo = P->g.lo;
+  *hi = P->g.hi;
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_hi, int64_t* lo, int64_t* hi,
+                                int64_t* n_unknowns) {
+  if (!desc) return fail(B200CG_ERR_INVALID_ARG, "desc is NULL");
+  b200cg_plan_s tmp;
+  tmp.desc = *desc;
+  RET(setup_geometry(&tmp));
+  if (y_lo) *y_lo = tmp.g.ylo;
+  if (y_hi) *y_hi = tmp.g.yhi;
+  if (lo) *lo = tmp.g.lo;
+  if (hi) *hi = tmp.g.hi;
+  if (n_unknowns) *n_unknowns = tmp.n_global;
+  return B200CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- data movement
+static long long local_count(const b200cg_plan_s* P) { return P->g.hi - P->g.lo; }
+
+static int upload_vector(b200cg_plan_s* P, const double* host, double* pitched) {
+  const long long cnt = local_count(P);
+  CU(cudaMemcpyAsync(P->compact, host, cnt * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+  scatter_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, P->stream>>>(P->compact, pitched, P->g);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+static int download_vector(b200cg_plan_s* P, const double* pitched, double* host) {
+  const long long cnt = local_count(P);
+  gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, P->stream>>>(pitched, P->compact, P->g);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  return B200CG_OK;
+}
+static int ensure_u(b200cg_plan_s* P) {
+  if (!P->u) RET(alloc_vec(P, &P->u));
+  return B200CG_OK;
+}
+static int ensure_scratch(b200cg_plan_s* P) {
+  if (!P->va) RET(alloc_vec(P, &P->va));
+  if (!P->vb) RET(alloc_vec(P, &P->vb));
+  return B200CG_OK;
+}
+// one-row halo exchange of a pitched vector with the slab neighbours (no-op on a single GPU)
+static int exchange_halo(b200cg_plan_s* P, double* v) {
+  if (P->desc.world <= 1) return B200CG_OK;
+  std::string err;
+  const Geom& g = P->g;
+  double* first_owned = v + (size_t)1 * g.pitch;
+  double* last_owned = v + (size_t)(g.yrows - 2) * g.pitch;
+  double* halo_below = v;
+  double* halo_above = v + (size_t)(g.yrows - 1) * g.pitch;
+  if (!comm_halo(&P->comm, first_owned, last_owned, halo_below, halo_above, g.pitch, P->stream, &err))
+    return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_build_rhs(b200cg_plan_t P) {
+  if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  CU(cudaSetDevice(P->desc.device));
+  setup_kernel<<<ew_grid(P, local_count(P)), CTA_THREADS, 0, P->stream>>>(P->b, nullptr, P->g, 0);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(P->stream));
+  P->have_rhs = true;
+  return B200CG_OK;
+}
+extern "C" int b200cg_set_rhs(b200cg_plan_t P, const double* b_host) {
+  if (!P || !b_host) return fail(B200CG_ERR_INVALID_ARG, "plan/b_host is NULL");
+  CU(cudaSetDevice(P->desc.device));
+  RET(upload_vector(P, b_host, P->b));
+  CU(cudaStreamSynchronize(P->stream));
+  P->have_rhs = true;
+  return B200CG_OK;
+}
+extern "C" int b200cg_get_rhs(b200cg_plan_t P, double* b_host) {
+  if (!P || !b_host) return fail(B200CG_ERR_INVALID_ARG, "plan/b_host is NULL");
+  if (!P->have_rhs) return fail(B200CG_ERR_STATE, "no rhs in the plan: call b200cg_build_rhs or b200cg_set_rhs first");
+  CU(cudaSetDevice(P->desc.device));
+  RET(download_vector(P, P->b, b_host));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+static int setup_to_host(b200cg_plan_s* P, int what, double* host) {
+  const long long cnt = local_count(P);
+  setup_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, P->stream>>>(nullptr, P->compact, P->g, what);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+extern "C" int b200cg_get_true_solution(b200cg_plan_t P, double* u_host) {
+  if (!P || !u_host) return fail(B200CG_ERR_INVALID_ARG, "plan/u_host is NULL");
+  CU(cudaSetDevice(P->desc.device));
+  return setup_to_host(P, 1, u_host);
+}
+extern "C" int b200cg_get_coords(b200cg_plan_t P, double* xs, double* ys) {
+  if (!P || !xs || !ys) return fail(B200CG_ERR_INVALID_ARG, "plan/xs/ys is NULL");
+  CU(cudaSetDevice(P->desc.device));
+  RET(setup_to_host(P, 2, xs));
+  return setup_to_host(P, 3, ys);
+}
+
+// ------------------------------------------------------------------------------------------- operator
+template <int MODE, int PF, int FLAGS>
+static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  if (P->g.tiles <= 0) return B200CG_OK;
+  cg_tile_kernel<MODE, PF, FLAGS><<<P->g.tiles, CTA_THREADS, 0, s>>>(a);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+
+static TileArgs base_args(b200cg_plan_s* P) {
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.st = P->d_state;
+  a.partials = P->d_partials;
+  a.cb_log = P->d_log;
+  a.defer = P->desc.world > 1 ? 1 : 0;
+  a.g = P->g;
+  return a;
+}
+
+// sharded plans: all-reduce this rank's totals, then every rank forms the same scalars (finalize_kernel)
+static int reduce_and_finalize(b200cg_plan_s* P, int which, int flags, bool with_max, cudaStream_t s) {
+  if (P->desc.world <= 1) return B200CG_OK;
+  std::string err;
+  if (!comm_allreduce_state(&P->comm, P->d_state, with_max, s, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, which, flags);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+
+constexpr int PF_DOT = 4;
+constexpr int PF_UPD = 3;
+constexpr int PF_APPLY = 4;
+
+extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_host) {
+  if (!P || !x_host || !y_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host/y_host is NULL");
+  CU(cudaSetDevice(P->desc.device));
+  RET(ensure_scratch(P));
+  RET(upload_vector(P, x_host, P->va));
+  RET(exchange_halo(P, P->va));
+  TileArgs a = base_args(P);
+  a.p_in = P->va;
+  a.out = P->vb;
+  RET((launch_tile<MODE_APPLY, PF_APPLY, 0>(P, a, P->stream)));
+  RET(download_vector(P, P->vb, y_host));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- CSR entry points
+extern "C" int b200cg_set_csr(b200cg_plan_t P, int64_t nrows, int64_t nnz, const int* row_map, const int* entries,
+                              const double* values) {
+  if (!P || !row_map || !entries || !values) return fail(B200CG_ERR_INVALID_ARG, "NULL argument");
+  if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
+  if (nrows != P->n_global) return fail(B200CG_ERR_INVALID_ARG, "nrows %lld != unknowns %lld", (long long)nrows, (long long)P->n_global);
+  CU(cudaSetDevice(P->desc.device));
+  std::string err;
+  int rc = csr_upload(&P->csr, nrows, nnz, row_map, entries, values, P->stream, &err);
+  if (rc) return fail(rc, "%s", err.c_str());
+  return B200CG_OK;
+}
+extern "C" int b200cg_assemble_csr(b200cg_plan_t P, int64_t* nnz) {
+  if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
+  CU(cudaSetDevice(P->desc.device));
+  std::string err;
+  int rc = csr_assemble(&P->csr, P->g, P->n_global, P->sms, P->stream, &err);
+  if (rc) return fail(rc, "%s", err.c_str());
+  if (nnz) *nnz = P->csr.nnz;
+  return B200CG_OK;
+}
+extern "C" int b200cg_get_csr(b200cg_plan_t P, int* row_map, int* entries, double* values) {
+  if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  if (!P->csr.row_map) return fail(B200CG_ERR_STATE, "no CSR matrix in the plan");
+  CU(cudaSetDevice(P->desc.device));
+  if (row_map) CU(cudaMemcpy(row_map, P->csr.row_map, (P->csr.nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (entries) CU(cudaMemcpy(entries, P->csr.entries, P->csr.nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  if (values) CU(cudaMemcpy(values, P->csr.values, P->csr.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  return B200CG_OK;
+}
+extern "C" int b200cg_csr_apply(b200cg_plan_t P, const double* x_host, double* y_host) {
+  if (!P || !x_host || !y_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host/y_host is NULL");
+  if (!P->csr.row_map) return fail(B200CG_ERR_STATE, "no CSR matrix in the plan");
+  CU(cudaSetDevice(P->desc.device));
+  std::string err;
+  int rc = csr_ensure_vectors(&P->csr, P->stream, &err);
+  if (rc) return fail(rc, "%s", err.c_str());
+  const long long N = P->csr.nrows;
+  CU(cudaMemcpyAsync(P->csr.z[0], x_host, N * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+  csr_spmv_kernel<0><<<csr_grid(N, P->sms), CTA_THREADS, 0, P->stream>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(y_host, P->csr.Az, N * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- solve
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4 };
+
+// Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
+// read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
+static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
+  cudaStream_t s = P->stream;
+  const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR;
+  int kernels = 0;
+  CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = B200CG_OK;
+  for (int k = 0; k < iters && rc == B200CG_OK; ++k) {
+    const int par = k & 1;
+    if (k == 0) cudaEventRecordWithFlags(P->ev[0], s, cudaEventRecordExternal);
+    if (csr) {
+      // assembled path: p update + SpMV + dots, then the shared update pass
+      csr_spmv_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+          csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+      if (with_u)
+        csr_update_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      else
+        csr_update_kernel<0><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+      continue;
+    }
+    TileArgs a = base_args(P);
+    a.r_in = P->r[par];
+    a.p_in = P->p[par];
+    a.x = P->x;
+    a.r_out = P->r[par ^ 1];
+    a.p_out = P->p[par ^ 1];
+    a.u = P->u;
+    const int fl = (with_u ? F_U : 0) | (report ? F_REPORT : 0);
+    rc = launch_tile<MODE_DOT, PF_DOT, 0>(P, a, s);
+    ++kernels;
+    if (rc == B200CG_OK && P->desc.world > 1) {
+      rc = reduce_and_finalize(P, 1, fl, false, s);
+      ++kernels;
+    }
+    if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+    if (rc != B200CG_OK) break;
+    if (report && with_u) rc = launch_tile<MODE_UPD, PF_UPD, F_REPORT | F_U>(P, a, s);
+    else if (report) rc = launch_tile<MODE_UPD, PF_UPD, F_REPORT>(P, a, s);
+    else if (with_u) rc = launch_tile<MODE_UPD, PF_UPD, F_U>(P, a, s);
+    else rc = launch_tile<MODE_UPD, PF_UPD, 0>(P, a, s);
+    ++kernels;
+    if (rc == B200CG_OK && P->desc.world > 1) {
+      rc = reduce_and_finalize(P, 2, fl, true, s);
+      ++kernels;
+      if (rc == B200CG_OK) rc = exchange_halo(P, P->r[par ^ 1]);
+      if (rc == B200CG_OK) rc = exchange_halo(P, P->p[par ^ 1]);
+    }
+    if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+    if (rc == B200CG_OK && report) {
+      TileArgs ra = base_args(P);
+      ra.p_in = P->x;
+      ra.r_in = P->b;
+      ra.u = P->u;
+      if (P->desc.world > 1) rc = exchange_halo(P, P->x);
+      if (rc == B200CG_OK)
+        rc = with_u ? launch_tile<MODE_APPLY, PF_APPLY, F_REPORT | F_U>(P, ra, s)
+                    : launch_tile<MODE_APPLY, PF_APPLY, F_REPORT>(P, ra, s);
+      ++kernels;
+      if (rc == B200CG_OK && P->desc.world > 1) {
+        rc = reduce_and_finalize(P, 3, fl, false, s);
+        ++kernels;
+      }
+    }
+  }
+  cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != B200CG_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(B200CG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(B200CG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  out->exec = exec;
+  out->iters = iters;
+  out->kernels = kernels;
+  return B200CG_OK;
+}
+
+static int default_iters_per_graph(const b200cg_plan_s* P) {
+  // small grids are launch-bound: long graphs; big grids: keep the stop/interrupt latency around 0.1 s
+  const long long n = local_count(P);
+  if (n <= (1LL << 20)) return 100;
+  if (n <= (1LL << 24)) return 50;
+  return 20;
+}
+
+extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
+                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
+                            const volatile int* stop_flag) {
+  if (!P || !prm || !info) return fail(B200CG_ERR_INVALID_ARG, "plan/params/info is NULL");
+  if (prm->op != B200CG_OP_MATRIX_FREE && prm->op != B200CG_OP_CSR) return fail(B200CG_ERR_INVALID_ARG, "unknown operator %d", prm->op);
+  if (prm->rule != B200CG_RULE_REL_L2 && prm->rule != B200CG_RULE_MAXNORM) return fail(B200CG_ERR_INVALID_ARG, "unknown rule %d", prm->rule);
+  if (!prm->rhs_on_device && !b_host) return fail(B200CG_ERR_INVALID_ARG, "b_host is NULL and rhs_on_device is 0");
+  if (prm->rhs_on_device && !P->have_rhs) return fail(B200CG_ERR_STATE, "rhs_on_device set but the plan holds no rhs");
+  if (!prm->keep_x_on_device && !x_host) return fail(B200CG_ERR_INVALID_ARG, "x_host is NULL and keep_x_on_device is 0");
+  const bool csr = prm->op == B200CG_OP_CSR;
+  if (csr && !P->csr.row_map) return fail(B200CG_ERR_STATE, "CSR solve without a matrix: call b200cg_set_csr / b200cg_assemble_csr");
+  if (csr && prm->rule == B200CG_RULE_REL_L2 && cb) return fail(B200CG_ERR_UNSUPPORTED, "per-iteration report callbacks exist only on the matrix-free path");
+  memset(info, 0, sizeof(*info));
+  const double t_begin = now_ms();
+  CU(cudaSetDevice(P->desc.device));
+  cudaStream_t s = P->stream;
+  const long long cnt = local_count(P);
+  info->local_unknowns = cnt;
+  P->have_solution = false;
+
+  // ---- inputs
+  CU(cudaEventRecord(P->ev[3], s));
+  if (!prm->rhs_on_device) {
+    RET(upload_vector(P, b_host, P->b));
+    P->have_rhs = true;
+    info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    info->kernel_launches += 1;
+  }
+  const bool with_u = (u_host != nullptr);
+  if (with_u) {
+    RET(ensure_u(P));
+    RET(upload_vector(P, u_host, P->u));
+    info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    info->kernel_launches += 1;
+  }
+  P->have_u = with_u;
+  CU(cudaEventRecord(P->ev[4], s));
+
+  // ---- device-side solver state
+  const bool report = (prm->rule == B200CG_RULE_REL_L2) && (cb != nullptr);
+  DevState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.eps_rel = prm->eps_rel;
+  hs.eps_p = prm->eps_p;
+  hs.eps_r = prm->eps_r;
+  hs.eps_e = prm->eps_e;
+  hs.max_it = prm->max_it;
+  hs.rule = prm->rule;
+  hs.has_u = with_u ? 1 : 0;
+  hs.callback_every = (cb && prm->rule == B200CG_RULE_MAXNORM) ? (prm->callback_every > 0 ? prm->callback_every : 100) : 0;
+  *P->h_state = hs;
+  CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
+
+  if (csr) {
+    std::string err;
+    int rc = csr_ensure_vectors(&P->csr, s, &err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    // the assembled path works on compact vectors: gather b (and u) out of the pitched copies
+    gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
+    if (with_u) gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->u, P->csr.u, P->g);
+    P->csr.has_u = with_u;
+    csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+    CU(cudaGetLastError());
+    info->kernel_launches += 2 + (with_u ? 1 : 0);
+  } else {
+    const Geom& g = P->g;
+    InitArgs ia;
+    ia.b = P->b;
+    ia.u = with_u ? P->u : nullptr;
+    ia.r = P->r[0];
+    ia.p = P->p[0];
+    ia.x = P->x;
+    ia.st = P->d_state;
+    ia.partials = P->d_partials;
+    ia.cb_log = P->d_log;
+    ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
+    ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
+    ia.defer = P->desc.world > 1 ? 1 : 0;
+    cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
+    CU(cudaGetLastError());
+    info->kernel_launches += 1;
+    if (P->desc.world > 1) {
+      RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
+      RET(exchange_halo(P, P->r[0]));
+      RET(exchange_halo(P, P->p[0]));
+      info->kernel_launches += 1;
+    }
+  }
+
+  // ---- the captured loop
+  int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
+  if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
+  K = std::max(2, (K + 1) & ~1);
+  K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
+  const int variant = (with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0);
+  const int key = variant * 4096 + K;
+  GraphEntry& ge = P->graphs[key];
+  if (!ge.exec) RET(build_graph(P, variant, K, &ge));
+
+  CU(cudaEventRecord(P->ev[5], s));
+  unsigned int consumed = 0;
+  bool interrupted = false;
+  double dot_ms = 0.0, upd_ms = 0.0;
+  int samples = 0;
+  // the init kernel's verdict (0 iterations) and record come back with the first graph launch
+  for (;;) {
+    CU(cudaGraphLaunch(ge.exec, s));
+    info->kernel_launches += ge.kernels;
+    CU(cudaStreamSynchronize(s));
+    const DevState& st = *P->h_state;
+    if (consumed == 0 && st.it > 0) {  // kernels of the first captured iteration really ran in this launch
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, P->ev[0], P->ev[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&b, P->ev[1], P->ev[2]) == cudaSuccess) {
+        dot_ms += a;
+        upd_ms += b;
+        ++samples;
+      }
+    } else if (st.it > 0 && !st.done) {
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, P->ev[0], P->ev[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&b, P->ev[1], P->ev[2]) == cudaSuccess) {
+        dot_ms += a;
+        upd_ms += b;
+        ++samples;
+      }
+    }
+    if (cb) {
+      for (; consumed < st.n_log; ++consumed) {
+        const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
+        cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
+      }
+    } else {
+      consumed = st.n_log ? st.n_log : 1;
+    }
+    if (consumed == 0) consumed = 1;
+    if (st.done) break;
+    if (stop_flag && *stop_flag) {
+      interrupted = true;
+      break;
+    }
+  }
+  CU(cudaEventRecord(P->ev[6], s));
+
+  // ---- outputs
+  const DevState st = *P->h_state;
+  if (csr) {
+    // scatter the compact solution into the pitched x so that postprocess / get_solution see one layout
+    scatter_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->csr.x, P->x, P->g);
+    info->kernel_launches += 1;
+  }
+  if (!prm->keep_x_on_device) {
+    RET(download_vector(P, P->x, x_host));
+    info->d2h_bytes += cnt * (int64_t)sizeof(double);
+    info->kernel_launches += 1;
+  }
+  CU(cudaEventRecord(P->ev[7], s));
+  CU(cudaStreamSynchronize(s));
+  P->have_solution = true;
+
+  info->iterations = st.it;
+  info->converged = interrupted ? 0 : st.converged;
+  info->stop_reason = interrupted ? B200CG_STOP_INTERRUPTED : st.stop_reason;
+  info->r0_l2 = st.r0_norm;
+  info->r_l2 = st.r_norm;
+  info->r_max = st.r_max;
+  info->dx_max = st.dx_max;
+  info->err_max = st.err_max;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, P->ev[3], P->ev[4]);
+  info->h2d_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[5], P->ev[6]);
+  info->solve_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[6], P->ev[7]);
+  info->d2h_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[3], P->ev[7]);
+  info->device_ms = ms;
+  info->dot_kernel_ms = samples ? dot_ms / samples : 0.0;
+  info->upd_kernel_ms = samples ? upd_ms / samples : 0.0;
+  info->kernel_samples = samples;
+  // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
+  if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);
+  info->total_ms = now_ms() - t_begin;
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_get_solution(b200cg_plan_t P, double* x_host) {
+  if (!P || !x_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host is NULL");
+  if (!P->have_solution) return fail(B200CG_ERR_STATE, "no solution in the plan: call b200cg_solve first");
+  CU(cudaSetDevice(P->desc.device));
+  RET(download_vector(P, P->x, x_host));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host, double* error_host) {
+  if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  if (!P->have_solution) return fail(B200CG_ERR_STATE, "no solution in the plan: call b200cg_solve first");
+  CU(cudaSetDevice(P->desc.device));
+  cudaStream_t s = P->stream;
+  const long long cnt = local_count(P);
+  if (residual_host) {
+    if (op == B200CG_OP_CSR) {
+      if (!P->csr.row_map) return fail(B200CG_ERR_STATE, "no CSR matrix in the plan");
+      // A x - b with the assembled matrix (dirichlet_solver.cpp:147-161): z[0] <- x, Az <- A x - b
+      csr_residual_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(residual_host, P->csr.Az, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      RET(ensure_scratch(P));
+      RET(exchange_halo(P, P->x));
+      TileArgs a = base_args(P);
+      a.p_in = P->x;
+      a.r_in = P->b;
+      a.out = P->vb;
+      RET((launch_tile<MODE_APPLY, PF_APPLY, F_SUB_B>(P, a, s)));
+      RET(download_vector(P, P->vb, residual_host));
+    }
+  }
+  if (error_host) {
+    if (!P->have_u) return fail(B200CG_ERR_STATE, "error = x - u needs the true solution passed to the last solve");
+    gather_diff_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->x, P->u, P->compact, P->g);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(error_host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  return B200CG_OK;
+}

@@ -1,0 +1,27 @@
+// Row-slab sharding plumbing: one process per GPU, NCCL resolved at run time (dlopen), so that the single-GPU
+// path has no NCCL dependency and the library loads on machines without it.
+// Per iteration: all-reduce of the dot-phase sums, all-reduce of the update-phase sums and maxima,
+// one-row halo exchange of r and p with the slab neighbours - all captured in the iteration graph.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "common.cuh"
+
+namespace b200cg {
+
+struct Comm {
+  void* lib = nullptr;
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1;
+};
+
+bool comm_unique_id(void* id128, std::string* err);
+bool comm_init(Comm* c, const void* id128, int rank, int world, cudaStream_t s, std::string* err);
+void comm_destroy(Comm* c);
+// exchange one row (count doubles) with both neighbours: send first/last owned rows, receive into the halo rows
+bool comm_halo(Comm* c, const double* first_owned, const double* last_owned, double* halo_below, double* halo_above,
+               int count, cudaStream_t s, std::string* err);
+// in-place all-reduce of st->loc_s (sum, 4 doubles) and optionally st->loc_m (max, 4 doubles)
+bool comm_allreduce_state(Comm* c, DevState* st, bool with_max, cudaStream_t s, std::string* err);
+
+}  // namespace b200cg

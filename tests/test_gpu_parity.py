@@ -1,0 +1,340 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every call goes through the C ABI (libb200cg.so via
+the ctypes mirror); the CPU oracle and the committed golden fixtures are the checkers.
+
+Bars (BASELINE.json north_star): iteration count within +-1 of the reference, final residual and solution
+max-abs difference within 1e-10 relative in fp64. Element-wise operations (apply, CSR assembly, axpys) are
+expected to be numerically identical; only dot-product summation order differs.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10  # the north-star tolerance
+DOMAINS = {0: (0.0, 1.0), 1: (1.0, 2.0)}
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from iterative_solvers_b200 import capi as c
+
+    c.lib()  # raises if the CUDA library was not built: no fallback
+    assert c.device_count() >= 1, "these tests need a CUDA device"
+    return c
+
+
+def plan_for(capi, n, a_tag=0, domain=0, **kw):
+    a, b = DOMAINS[a_tag]
+    return capi.Plan(n, n, a, b, a, b, domain=domain, **kw)
+
+
+def oracle_for(oracle_mod, n, a_tag=0, kind=0, m=None):
+    a, b = DOMAINS[a_tag]
+    return oracle_mod.Oracle(m or n, n, a, b, a, b, kind)
+
+
+def relmax(x, ref):
+    return np.max(np.abs(x - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+def ulp_diff(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.spacing(np.abs(b)), 1e-300))
+
+
+# ---------------------------------------------------------------- K0: rhs, true solution, coordinates
+@pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1), (128, 0), (128, 1)])
+def test_setup_vectors(capi, golden_ref, n, a_tag):
+    with plan_for(capi, n, a_tag) as p:
+        tag = f"mf_n{n}_a{a_tag}"
+        assert p.N == len(golden_ref[tag + "_rhs"])
+        p.build_rhs()
+        b = p.get_rhs()
+        ref = golden_ref[tag + "_rhs"]
+        # device exp() vs glibc exp(): a few ulp of the largest term; boundary terms are O(1/h^2) * u
+        assert np.max(np.abs(b - ref)) <= 8 * np.spacing(np.max(np.abs(ref)))
+        assert relmax(b, ref) < 1e-14
+        u = p.true_solution()
+        assert ulp_diff(u, golden_ref[tag + "_true"]) <= 4
+        if (n, a_tag) in ((6, 1), (30, 1), (128, 0)):
+            xs, ys = p.coords()
+            assert np.array_equal(xs, golden_ref[f"grid_n{n}_a{a_tag}_xs"])
+            assert np.array_equal(ys, golden_ref[f"grid_n{n}_a{a_tag}_ys"])
+
+
+def test_set_get_rhs_roundtrip(capi):
+    with plan_for(capi, 30) as p:
+        v = np.random.default_rng(1).standard_normal(p.N)
+        p.set_rhs(v)
+        assert np.array_equal(p.get_rhs(), v)
+
+
+# ---------------------------------------------------------------- apply
+@pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1), (64, 0), (128, 0), (128, 1)])
+def test_apply_matches_reference_fixture(capi, golden_ref, n, a_tag):
+    with plan_for(capi, n, a_tag) as p:
+        tag = f"mf_n{n}_a{a_tag}"
+        y = p.apply(golden_ref[tag + "_apply_in"])
+        assert np.array_equal(y, golden_ref[tag + "_apply_out"])  # same operations in the same order
+
+
+def test_apply_reproduces_check_py_matrix(capi, golden_scripts):
+    with plan_for(capi, 6, 1) as p:
+        cols = np.stack([p.apply(np.eye(16)[j]) for j in range(16)], axis=1)
+        assert np.array_equal(cols, golden_scripts["check_matrix"])
+
+
+@pytest.mark.parametrize("n,domain,tile_rows", [(600, 0, 0), (1030, 0, 7), (1030, 0, 1), (512, 0, 64), (1009, 1, 5),
+                                                (505, 1, 0), (4, 0, 0), (2, 1, 0), (3, 1, 0)])
+def test_apply_vs_oracle_across_strips_and_tiles(capi, oracle_mod, n, domain, tile_rows):
+    """Grids wider than one 504-column strip, ragged tile heights, both domain kinds, smallest grids."""
+    o = oracle_for(oracle_mod, n, 0, domain)
+    with plan_for(capi, n, 0, domain, tile_rows=tile_rows) as p:
+        assert p.N == o.N
+        x = np.random.default_rng(n).standard_normal(o.N)
+        assert np.array_equal(p.apply(x), o.apply(x))
+
+
+def test_apply_rect_nonsquare(capi, oracle_mod):
+    o = oracle_mod.Oracle(37, 1200, 0.0, 2.0, -1.0, 0.5, 1)  # m=37, n=1200
+    with capi.Plan(37, 1200, 0.0, 2.0, -1.0, 0.5, domain=1) as p:
+        x = np.random.default_rng(5).standard_normal(o.N)
+        assert np.array_equal(p.apply(x), o.apply(x))
+
+
+# ---------------------------------------------------------------- MatrixFreeSolver path
+def test_two_iterations_match_py_debug(capi, golden_scripts, golden_ref):
+    """The reference's own known answer: x2 of py_debug.txt:14 (script RHS rounded to 8 decimals)."""
+    with plan_for(capi, 6, 1) as p:
+        x, info = p.solve(b=golden_scripts["check_debug_rhs"], eps_rel=1e-9, max_it=2)
+        assert info["iterations"] == 2 and not info["converged"]
+        assert np.max(np.abs(x - golden_scripts["py_x2"])) < 1e-13
+        x, info = p.solve(b=golden_ref["mf_n6_a1_rhs"], eps_rel=1e-8, max_it=2)
+        assert relmax(x, golden_ref["mf_n6_a1_x2"]) < 1e-14
+
+
+@pytest.mark.parametrize("n,a_tag,iters", [(6, 1, 13), (30, 1, 88), (64, 0, 178), (128, 0, 352), (128, 1, 362)])
+def test_matrix_free_solve_parity(capi, golden_ref, n, a_tag, iters):
+    tag = f"mf_n{n}_a{a_tag}"
+    with plan_for(capi, n, a_tag) as p:
+        x, info = p.solve(b=golden_ref[tag + "_rhs"], eps_rel=1e-8, max_it=10000)
+        assert abs(info["iterations"] - iters) <= 1
+        assert info["converged"]
+        assert relmax(x, golden_ref[tag + "_x"]) < REL
+        assert info["r_l2"] <= 1e-8 * info["r0_l2"]
+        # config 1 pins
+        if (n, a_tag) == (128, 0):
+            assert info["iterations"] == 352
+            assert abs(info["r0_l2"] - 5.187466787388469e5) < 1e-6
+        # device-built rhs instead of the host one: still inside the bar
+        p.build_rhs()
+        x2, info2 = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=10000)
+        assert abs(info2["iterations"] - iters) <= 1
+        assert relmax(x2, golden_ref[tag + "_x"]) < REL
+
+
+def test_matrix_free_solver_callback_history(capi, golden_ref):
+    """Registered callback: (it, ||dx||_2, recomputed ||b-Ax||_2, ||x-u||_2) every iteration
+    (matrix_free_system.cpp:444-468)."""
+    for n, a_tag in [(6, 1), (30, 1)]:
+        tag = f"mf_n{n}_a{a_tag}"
+        hist = golden_ref[tag + "_hist"]
+        got = []
+        with plan_for(capi, n, a_tag) as p:
+            x, info = p.solve(b=golden_ref[tag + "_rhs"], u=golden_ref[tag + "_true"], eps_rel=1e-8,
+                              max_it=10000, callback=lambda it, pr, rs, er: got.append((it, pr, rs, er)))
+        assert info["iterations"] == len(hist) == len(got)
+        got = np.array(got)
+        assert np.array_equal(got[:, 0], np.arange(len(hist)))
+        scale = np.max(np.abs(hist), axis=0)
+        assert np.all(np.abs(got[:, 1:] - hist) <= 1e-9 * scale + 1e-9 * np.abs(hist))
+        assert relmax(x, golden_ref[tag + "_x"]) < REL
+
+
+def test_solve_edge_cases(capi):
+    with plan_for(capi, 30) as p:
+        zero = np.zeros(p.N)
+        x, info = p.solve(b=zero, eps_rel=1e-8, max_it=100)  # r0 = 0: loop never entered, "converged"
+        assert info["iterations"] == 0 and info["converged"] and np.all(x == 0)
+        p.build_rhs()
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=0)
+        assert info["iterations"] == 0 and not info["converged"] and np.all(x == 0)
+        x, info = p.solve(rhs_on_device=True, eps_rel=2.0, max_it=50)  # eps >= 1: satisfied at once
+        assert info["iterations"] == 0 and info["converged"]
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=7)  # odd cap inside one graph launch
+        assert info["iterations"] == 7 and not info["converged"] and info["stop_reason"] == "ITERATIONS"
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=7, iters_per_graph=2)
+        assert info["iterations"] == 7
+
+
+def test_tile_height_and_graph_length_do_not_change_the_answer(capi, oracle_mod):
+    o = oracle_for(oracle_mod, 64)
+    ref = o.mf_solve(eps=1e-9, max_it=10000)
+    for tile_rows, k in [(1, 2), (5, 6), (64, 100), (0, 0)]:
+        with plan_for(capi, 64, tile_rows=tile_rows) as p:
+            x, info = p.solve(b=o.rhs(), eps_rel=1e-9, max_it=10000, iters_per_graph=k)
+            assert abs(info["iterations"] - ref["iterations"]) <= 1
+            assert relmax(x, ref["x"]) < REL
+
+
+def test_interrupt_flag(capi):
+    with plan_for(capi, 128) as p:
+        p.build_rhs()
+        flag = ctypes.c_int(1)
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, iters_per_graph=10, stop_flag=flag)
+        assert info["stop_reason"] == "INTERRUPTED" and not info["converged"]
+        assert 0 < info["iterations"] <= 10
+
+
+# ---------------------------------------------------------------- MSGSolver rules (max-norm), both operators
+@pytest.mark.parametrize("op", [0, 1])
+@pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1), (128, 0)])
+def test_maxnorm_rules_parity(capi, golden_ref, n, a_tag, op):
+    tag = f"grid_n{n}_a{a_tag}"
+    eps = 1e-6 if n <= 30 else 1e-8
+    with plan_for(capi, n, a_tag) as p:
+        if op == 1:
+            p.assemble_csr()
+        for cname, kw in {"pr": dict(eps_p=eps, eps_r=eps), "r": dict(eps_p=-1.0, eps_r=eps)}.items():
+            info_ref = golden_ref[f"{tag}_msg_{cname}_info"]
+            cb_ref = golden_ref[f"{tag}_msg_{cname}_cb"]
+            got = []
+            x, info = p.solve(b=golden_ref[tag + "_rhs"], u=golden_ref[tag + "_true"], op=op,
+                              rule=capi.RULE_MAXNORM, max_it=10000,
+                              callback=lambda it, pr, rs, er: got.append((it, pr, rs, er)), **kw)
+            assert abs(info["iterations"] - int(info_ref[0])) <= 1
+            assert info["converged"] == bool(info_ref[1])
+            assert info["stop_reason"] == capi.STOP_NAMES[int(info_ref[2])]
+            assert relmax(x, golden_ref[f"{tag}_msg_{cname}_x"]) < REL
+            if info["iterations"] == int(info_ref[0]):
+                assert abs(info["r_max"] - info_ref[3]) <= 1e-6 * abs(info_ref[3])
+                assert abs(info["err_max"] - info_ref[5]) <= 1e-9 * abs(info_ref[5])
+                # callback cadence: it 0, 1, every 100, final (msg_solver.cpp:75,172,193)
+                got = np.array(got)
+                assert np.array_equal(got[:, 0], cb_ref[:, 0])
+                assert got[0, 1] == cb_ref[0, 1] == np.finfo(np.float64).max
+                assert np.allclose(got[1:, 1:], cb_ref[1:, 1:], rtol=1e-6, atol=0)
+
+
+def test_maxnorm_without_true_solution(capi, oracle_mod):
+    o = oracle_for(oracle_mod, 30, 1)
+    ref = o.msg_solve(u=None, eps_p=1e-7, eps_r=-1.0, eps_e=1e-3, max_it=10000)  # eps_e ignored without u
+    with plan_for(capi, 30, 1) as p:
+        x, info = p.solve(b=o.rhs(), rule=capi.RULE_MAXNORM, eps_p=1e-7, eps_r=-1.0, eps_e=1e-3, max_it=10000)
+        assert info["iterations"] == ref["iterations"] and info["stop_reason"] == ref["stop_reason"]
+        assert info["err_max"] == np.finfo(np.float64).max
+        assert relmax(x, ref["x"]) < REL
+
+
+def test_exact_error_rule(capi, oracle_mod):
+    o = oracle_for(oracle_mod, 30, 1)
+    u = o.true_solution()
+    ref = o.msg_solve(u=u, eps_p=-1.0, eps_r=-1.0, eps_e=5e-3, max_it=10000)
+    assert ref["stop_reason"] == "EXACT_ERROR"
+    for op in (0, 1):
+        with plan_for(capi, 30, 1) as p:
+            if op:
+                p.assemble_csr()
+            x, info = p.solve(b=o.rhs(), u=u, op=op, rule=capi.RULE_MAXNORM, eps_e=5e-3, max_it=10000)
+            assert info["stop_reason"] == "EXACT_ERROR" and abs(info["iterations"] - ref["iterations"]) <= 1
+            assert relmax(x, ref["x"]) < 1e-9
+
+
+# ---------------------------------------------------------------- CSR path
+@pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1)])
+def test_csr_assembly_matches_reference(capi, golden_ref, n, a_tag):
+    tag = f"grid_n{n}_a{a_tag}"
+    with plan_for(capi, n, a_tag) as p:
+        nnz = p.assemble_csr()
+        assert [p.N, nnz] == list(golden_ref[tag + "_shape"])
+        row_map, entries, values = p.get_csr(nnz)
+        assert np.array_equal(row_map, golden_ref[tag + "_row_map"])
+        assert np.array_equal(entries, golden_ref[tag + "_entries"])  # per-row order diag, L, R, T, B
+        assert np.array_equal(values, golden_ref[tag + "_values"])
+
+
+@pytest.mark.parametrize("n,domain", [(128, 0), (700, 0), (333, 1)])
+def test_csr_assembly_and_spmv_vs_oracle(capi, oracle_mod, n, domain):
+    o = oracle_for(oracle_mod, n, 0, domain)
+    csr = o.csr()
+    with plan_for(capi, n, 0, domain) as p:
+        nnz = p.assemble_csr()
+        got = p.get_csr(nnz)
+        for a, b in zip(got, csr):
+            assert np.array_equal(a, b)
+        x = np.random.default_rng(n).standard_normal(o.N)
+        y = p.csr_apply(x)
+        assert np.array_equal(y, o.spmv(csr, x))
+        assert np.array_equal(y, p.apply(x))  # both operators accumulate in the same order
+        # caller-supplied matrix (what MSGSolver receives)
+        p.set_csr(*csr)
+        assert np.array_equal(p.csr_apply(x), y)
+
+
+# ---------------------------------------------------------------- DirichletSolver post-processing
+def test_postprocess_matches_facade(capi, golden_ref):
+    for op in (0, 1):
+        with plan_for(capi, 30, 1) as p:
+            if op:
+                p.assemble_csr()
+            x, info = p.solve(b=golden_ref["grid_n30_a1_rhs"], u=golden_ref["grid_n30_a1_true"], op=op,
+                              rule=capi.RULE_MAXNORM, eps_p=1e-6, eps_r=1e-6, max_it=10000)
+            res, err = p.postprocess(op=op)
+            assert info["iterations"] == int(golden_ref["dirichlet_n30_info"][0])
+            assert relmax(x, golden_ref["dirichlet_n30_solution"]) < REL
+            ref_res = golden_ref["dirichlet_n30_residual"]
+            # residual = A x - b: differences in x are amplified by |A| ~ 1e4
+            assert np.max(np.abs(res - ref_res)) <= 1e-10 * np.max(np.abs(golden_ref["grid_n30_a1_rhs"]))
+            assert np.max(np.abs(err - golden_ref["dirichlet_n30_error"])) <= REL * np.max(np.abs(x))
+            assert np.array_equal(p.get_solution(), x)
+
+
+# ---------------------------------------------------------------- RECT domain (parity unpinned: oracle only)
+@pytest.mark.parametrize("n", [33, 200])
+def test_rect_solve_vs_oracle(capi, oracle_mod, n):
+    o = oracle_for(oracle_mod, n, 0, 1)
+    ref = o.mf_solve(eps=1e-9, max_it=10000)
+    with plan_for(capi, n, 0, 1) as p:
+        x, info = p.solve(b=o.rhs(), eps_rel=1e-9, max_it=10000)
+        assert abs(info["iterations"] - ref["iterations"]) <= 1
+        assert relmax(x, ref["x"]) < REL
+        assert np.max(np.abs(x - o.true_solution())) < 1e-3  # O(h^2) against the analytic solution
+
+
+# ---------------------------------------------------------------- sizes of BASELINE.json
+def test_config2_fixed_iterations_vs_oracle(capi, oracle_mod):
+    """4096^2 (12.6 M unknowns): 5 iterations, x / ||r|| against the oracle at the same count."""
+    n = 4096
+    o = oracle_for(oracle_mod, n)
+    b = o.rhs()
+    ref = o.mf_solve(b=b, eps=1e-8, max_it=5)
+    with plan_for(capi, n) as p:
+        x, info = p.solve(b=b, eps_rel=1e-8, max_it=5)
+        assert info["iterations"] == 5
+        assert relmax(x, ref["x"]) < REL
+        assert abs(info["r_l2"] - ref["r_norm"]) <= REL * ref["r_norm"]
+        assert abs(info["r0_l2"] - ref["r0_norm"]) <= 1e-13 * ref["r0_norm"]
+        v = np.random.default_rng(0).standard_normal(o.N)
+        assert np.array_equal(p.apply(v), o.apply(v))
+
+
+def test_full_size_operator_properties(capi):
+    """16384^2-class properties that need no oracle: linearity, symmetry, negative definiteness, and a CG
+    run whose recurrence residual matches the recomputed one."""
+    n = 8192
+    with plan_for(capi, n) as p:
+        rng = np.random.default_rng(11)
+        x, y = rng.standard_normal(p.N), rng.standard_normal(p.N)
+        Ax, Ay = p.apply(x), p.apply(y)
+        assert abs(np.dot(x, Ay) - np.dot(y, Ax)) <= 1e-9 * abs(np.dot(x, Ay)) + 1e-3  # symmetric
+        assert np.dot(x, Ax) < 0  # negative definite Laplacian
+        Axy = p.apply(x + 2.0 * y)
+        assert np.max(np.abs(Axy - (Ax + 2.0 * Ay))) <= 1e-12 * np.max(np.abs(Axy))
+        p.build_rhs()
+        b = p.get_rhs()
+        xs, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=200)
+        assert info["iterations"] == 200 and info["r_l2"] < info["r0_l2"]
+        res, _ = p.postprocess(want_error=False)  # A x - b recomputed
+        assert abs(np.linalg.norm(res) - info["r_l2"]) <= 1e-8 * info["r0_l2"]
+        assert np.max(np.abs(res + (b - p.apply(xs)))) <= 1e-12 * np.max(np.abs(b))
