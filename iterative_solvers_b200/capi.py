@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libb200cg.so")
+LIB_PATH = os.environ.get("B200CG_LIB", os.path.join(PKG, "libb200cg.so"))
 
 DOMAIN_LSHAPE, DOMAIN_RECT = 0, 1
 OP_MATRIX_FREE, OP_CSR = 0, 1

@@ -60,6 +60,7 @@ struct b200cg_plan_s {
   b200cg_plan_desc desc;
   Geom g;
   int sms = 148;
+  int ctas_per_sm = 2;  // resident CTAs of the persistent sweep kernel per SM
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
   double* r[2] = {nullptr, nullptr};
@@ -156,7 +157,7 @@ static int setup_geometry(b200cg_plan_s* P) {
   g.hi = (g.yhi >= d.m) ? P->n_global : row_start(g, g.yhi);
   g.pitch = ((d.n + 1 + XOFF) + 15) / 16 * 16;
 
-  g.tile_rows = d.tile_rows > 0 ? d.tile_rows : 32;
+  g.tile_rows = d.tile_rows > 0 ? d.tile_rows : 64;
   g.strips = (d.n - 1) / STRIP_OUT + 1;
   g.stripB0 = (g.xsplit + 1) / STRIP_OUT;
   g.yB0 = g.ylo;
@@ -422,10 +423,29 @@ extern "C" int b200cg_get_coords(b200cg_plan_t P, double* xs, double* ys) {
 }
 
 // ------------------------------------------------------------------------------------------- operator
-template <int MODE, int PF, int FLAGS>
+// Stage geometry per kernel flavour: HS rows per stage, NST stages; ~96 KB of bulk-copy destinations per CTA
+// so that two CTAs stay resident per SM.
+template <int MODE, int FLAGS>
+struct StreamShape {
+  static constexpr int NSTREAM = StreamCfg<MODE, FLAGS>::NSTREAM;
+  static constexpr int HS = 2;
+  static constexpr int NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 6 : (NSTREAM == 3 ? 4 : 3));
+};
+
+template <int MODE, int FLAGS>
 static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
   if (P->g.tiles <= 0) return B200CG_OK;
-  cg_tile_kernel<MODE, PF, FLAGS><<<P->g.tiles, CTA_THREADS, 0, s>>>(a);
+  using Sh = StreamShape<MODE, FLAGS>;
+  auto kernel = cg_stream_kernel<MODE, FLAGS, Sh::HS, Sh::NST>;
+  constexpr size_t smem = stream_smem_bytes<MODE, FLAGS, Sh::HS, Sh::NST>();
+  static thread_local bool configured[64] = {};
+  const int dev = P->desc.device & 63;
+  if (!configured[dev]) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  const int grid = std::min(P->g.tiles, P->sms * P->ctas_per_sm);
+  kernel<<<grid, STREAM_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
 }
@@ -451,9 +471,6 @@ static int reduce_and_finalize(b200cg_plan_s* P, int which, int flags, bool with
   return B200CG_OK;
 }
 
-constexpr int PF_DOT = 4;
-constexpr int PF_UPD = 3;
-constexpr int PF_APPLY = 4;
 
 extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_host) {
   if (!P || !x_host || !y_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host/y_host is NULL");
@@ -464,7 +481,7 @@ extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_hos
   TileArgs a = base_args(P);
   a.p_in = P->va;
   a.out = P->vb;
-  RET((launch_tile<MODE_APPLY, PF_APPLY, 0>(P, a, P->stream)));
+  RET((launch_tile<MODE_APPLY, 0>(P, a, P->stream)));
   RET(download_vector(P, P->vb, y_host));
   CU(cudaStreamSynchronize(P->stream));
   return B200CG_OK;
@@ -555,7 +572,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     a.p_out = P->p[par ^ 1];
     a.u = P->u;
     const int fl = (with_u ? F_U : 0) | (report ? F_REPORT : 0);
-    rc = launch_tile<MODE_DOT, PF_DOT, 0>(P, a, s);
+    rc = launch_tile<MODE_DOT, 0>(P, a, s);
     ++kernels;
     if (rc == B200CG_OK && P->desc.world > 1) {
       rc = reduce_and_finalize(P, 1, fl, false, s);
@@ -563,10 +580,10 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     }
     if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
     if (rc != B200CG_OK) break;
-    if (report && with_u) rc = launch_tile<MODE_UPD, PF_UPD, F_REPORT | F_U>(P, a, s);
-    else if (report) rc = launch_tile<MODE_UPD, PF_UPD, F_REPORT>(P, a, s);
-    else if (with_u) rc = launch_tile<MODE_UPD, PF_UPD, F_U>(P, a, s);
-    else rc = launch_tile<MODE_UPD, PF_UPD, 0>(P, a, s);
+    if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
+    else if (report) rc = launch_tile<MODE_UPD, F_REPORT>(P, a, s);
+    else if (with_u) rc = launch_tile<MODE_UPD, F_U>(P, a, s);
+    else rc = launch_tile<MODE_UPD, 0>(P, a, s);
     ++kernels;
     if (rc == B200CG_OK && P->desc.world > 1) {
       rc = reduce_and_finalize(P, 2, fl, true, s);
@@ -582,8 +599,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       ra.u = P->u;
       if (P->desc.world > 1) rc = exchange_halo(P, P->x);
       if (rc == B200CG_OK)
-        rc = with_u ? launch_tile<MODE_APPLY, PF_APPLY, F_REPORT | F_U>(P, ra, s)
-                    : launch_tile<MODE_APPLY, PF_APPLY, F_REPORT>(P, ra, s);
+        rc = with_u ? launch_tile<MODE_APPLY, F_REPORT | F_U>(P, ra, s)
+                    : launch_tile<MODE_APPLY, F_REPORT>(P, ra, s);
       ++kernels;
       if (rc == B200CG_OK && P->desc.world > 1) {
         rc = reduce_and_finalize(P, 3, fl, false, s);
@@ -833,7 +850,7 @@ extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host
       a.p_in = P->x;
       a.r_in = P->b;
       a.out = P->vb;
-      RET((launch_tile<MODE_APPLY, PF_APPLY, F_SUB_B>(P, a, s)));
+      RET((launch_tile<MODE_APPLY, F_SUB_B>(P, a, s)));
       RET(download_vector(P, P->vb, residual_host));
     }
   }

@@ -1,0 +1,197 @@
+// Shared device helpers of libb200cg: modes, kernel arguments, reductions, scalar finalisation (sm_100a, fp64).
+//
+// Two fused kernels per CG iteration (DESIGN.md "Kernels"):
+//   dot phase    : p = r + beta*p_old on the fly, Ap = A p on the fly, reduces p.Ap and r.p       16 B/unknown
+//   update phase : same p / Ap recomputed, x += alpha p, r -= alpha Ap, stores x, r, p,
+//                  reduces r.r, |r|_inf, |dx|_inf (and |x-u|_inf)                                 48 B/unknown
+// Ap is never stored and p is never re-read: 64 B per unknown per iteration instead of the 80 B of the
+// store-Ap formulation. Every element-wise operation uses separately rounded multiplies and adds
+// in the reference's order (matrix_free_system.cpp:216-266, :422-438), so the iterates differ from the
+// reference's only through the summation order of the dot products.
+#pragma once
+#include <float.h>
+#include "common.cuh"
+
+namespace b200cg {
+
+enum { MODE_DOT = 0, MODE_UPD = 1, MODE_APPLY = 2 };
+enum {
+  F_U = 1,       // UPD / APPLY-report: also read the true solution u
+  F_REPORT = 2,  // UPD: reduce |dx|_2, |x-u|_2.  APPLY: reduce |b - A v|_2, append the callback record, no store
+  F_SUB_B = 4    // APPLY: out = A v - b
+};
+
+struct TileArgs {
+  const double* r_in;  // DOT/UPD: residual.  APPLY with F_SUB_B / F_REPORT: rhs b
+  const double* p_in;  // DOT/UPD: previous direction.  APPLY: input vector v
+  double* x;           // UPD
+  double* r_out;       // UPD
+  double* p_out;       // UPD
+  const double* u;     // F_U
+  double* out;         // APPLY
+  DevState* st;
+  double* partials;    // [MAX_PARTIALS][gridDim.x]
+  CbRecord* cb_log;
+  int defer;           // sharded plan: publish this rank's totals in st->loc_*, finalize after the all-reduce
+  Geom g;
+};
+
+// --------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ double2 ld_ro2(const double* p, bool ok) {
+  // read-only for the lifetime of the kernel: non-coherent path
+  return ok ? __ldg(reinterpret_cast<const double2*>(p)) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ double2 ld_rw2(const double* p, bool ok) {
+  return ok ? *reinterpret_cast<const double2*>(p) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reduction of NS sums and NM maxima (fixed tree: deterministic). Result valid in thread 0.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce(double (&s)[NS > 0 ? NS : 1], double (&mx)[NM > 0 ? NM : 1],
+                                             double* scratch /* [(NS+NM) * 32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = warp_sum(s[k]);
+#pragma unroll
+  for (int k = 0; k < NM; ++k) mx[k] = warp_max(mx[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) scratch[k * 32 + warp] = s[k];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) scratch[(NS + k) * 32 + warp] = mx[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double v = lane < nwarp ? scratch[k * 32 + lane] : 0.0;
+      s[k] = warp_sum(v);
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      double v = lane < nwarp ? scratch[(NS + k) * 32 + lane] : 0.0;
+      mx[k] = warp_max(v);
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-wide reduction: every CTA publishes its partials; the last CTA to arrive (ticket) sums them in index
+// order with a fixed tree, so the result does not depend on which CTA is last. Returns true in thread 0 of
+// that CTA with the totals in s / mx. Scalars never leave the device.
+template <int NS, int NM>
+__device__ __forceinline__ bool grid_reduce(double (&s)[NS > 0 ? NS : 1], double (&mx)[NM > 0 ? NM : 1],
+                                            double* partials, DevState* st, double* scratch) {
+  __shared__ bool is_last;
+  block_reduce<NS, NM>(s, mx, scratch);
+  const unsigned int nb = gridDim.x;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) partials[(size_t)k * nb + blockIdx.x] = s[k];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) partials[(size_t)(NS + k) * nb + blockIdx.x] = mx[k];
+    __threadfence();
+    unsigned int t = atomicAdd(&st->ticket, 1u);
+    is_last = (t == nb - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    double v = 0.0;
+    for (unsigned int i = threadIdx.x; i < nb; i += blockDim.x) v += __ldcg(&partials[(size_t)k * nb + i]);
+    s[k] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < NM; ++k) {
+    double v = 0.0;
+    for (unsigned int i = threadIdx.x; i < nb; i += blockDim.x)
+      v = fmax(v, __ldcg(&partials[(size_t)(NS + k) * nb + i]));
+    mx[k] = v;
+  }
+  block_reduce<NS, NM>(s, mx, scratch);
+  if (threadIdx.x == 0) st->ticket = 0u;
+  return threadIdx.x == 0;
+}
+
+__device__ __forceinline__ void append_record(DevState* st, CbRecord* log, double it, double p, double r,
+                                              double e) {
+  unsigned int k = st->n_log;
+  CbRecord rec;
+  rec.it = it; rec.precision = p; rec.residual = r; rec.error = e;
+  log[k % CB_LOG_CAP] = rec;
+  st->n_log = k + 1;
+}
+
+// alpha = r.r / p.Ap (matrix_free_system.cpp:417-419) or r.z / Az.z (msg_solver.cpp:96-102)
+__device__ __forceinline__ void finalize_dot(DevState* st, double pAp, double rz) {
+  st->pAp = pAp;
+  st->rz = rz;
+  st->alpha = (st->rule == 0) ? st->rr / pAp : rz / pAp;
+}
+
+// iteration_callback(iterations, precision, residual_norm, error_norm), matrix_free_system.cpp:457-468
+__device__ __forceinline__ void finalize_report(DevState* st, CbRecord* log, double res2, double err2, bool has_u) {
+  st->res_l2 = sqrt(res2);
+  if (has_u) st->err_l2 = sqrt(err2);
+  append_record(st, log, (double)(st->it - 1), st->dx_l2, st->res_l2, st->err_l2);
+  st->report_pending = 0;
+}
+
+// Stop rules, evaluated by one thread after the update phase.
+__device__ __forceinline__ void finalize_update(DevState* st, CbRecord* log, double rr_new, double r_max,
+                                                double dx_max, double err_max, double dx2, double err2,
+                                                bool report) {
+  const int it = st->it + 1;
+  st->it = it;
+  const double r_norm = sqrt(rr_new);
+  st->r_norm = r_norm;
+  st->r_max = r_max;
+  st->dx_max = dx_max;
+  if (st->has_u) st->err_max = err_max;
+  if (report) {
+    st->dx_l2 = sqrt(dx2);
+    st->err_l2 = sqrt(err2);
+    st->report_pending = 1;  // a report kernel follows
+  }
+  if (st->rule == 0) {
+    // MatrixFreeSolver, matrix_free_system.cpp:409,432-441,472
+    st->beta = rr_new / st->rr;
+    st->rr = rr_new;
+    const bool go = (it < st->max_it) && (r_norm > st->eps_rel * st->r0_norm);
+    if (!go) {
+      st->done = 1;
+      st->converged = (r_norm <= st->eps_rel * st->r0_norm) ? 1 : 0;
+      st->stop_reason = st->converged ? 2 : 0;
+    }
+  } else {
+    // MSGSolver, msg_solver.cpp:144-183
+    int done = 0;
+    if (st->eps_p > 0 && dx_max < st->eps_p) { done = 1; st->converged = 1; st->stop_reason = 1; }
+    else if (st->eps_r > 0 && r_max < st->eps_r) { done = 1; st->converged = 1; st->stop_reason = 2; }
+    else if (st->eps_e > 0 && st->has_u && err_max < st->eps_e) { done = 1; st->converged = 1; st->stop_reason = 3; }
+    if (!done) {
+      st->beta = (r_norm * r_norm) / st->rz;
+      st->rr = rr_new;
+      if (st->callback_every > 0 && (it % st->callback_every == 0 || it == 1))
+        append_record(st, log, (double)it, dx_max, r_max, st->err_max);
+      if (it >= st->max_it) { done = 1; st->converged = 0; st->stop_reason = 0; }
+    }
+    st->done = done;
+  }
+}
+
+}  // namespace b200cg

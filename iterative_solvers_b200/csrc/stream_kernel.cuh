@@ -1,0 +1,374 @@
+// The matrix-free hot kernel (sm_100a): a persistent, warp-specialised, bulk-async-copy fed stencil sweep.
+//
+//   producer warp : one elected lane walks this CTA's tiles and feeds a ring of shared-memory stages with
+//                   cp.async.bulk (UBLKCP) row copies of r, p_old (and x, u), completion counted by mbarriers
+//                   (expect_tx). No registers hold in-flight data; NST stages of HS rows are in flight per CTA.
+//   consumer warps: 8 warps, each thread owns 2 adjacent columns of a 512-column strip and marches down the
+//                   rows: p = r + beta*p_old for its columns, horizontal neighbours by warp shuffle (warp-edge
+//                   lanes recompute theirs from the staged r, p_old), vertical neighbours from registers.
+//                   Warps only meet at the stage mbarriers - there is no per-row __syncthreads.
+// A strip loads 4 extra columns on each side (one 32-byte sector), so every output column finds its
+// neighbours inside the CTA. Stage metadata written by the producer tells consumers what a stage holds, so the
+// tile order is the producer's business alone (static round-robin over a grid of resident CTAs).
+#pragma once
+#include <cuda/std/cstdint>
+#include "kernels_common.cuh"
+
+namespace b200cg {
+
+constexpr int CONS_WARPS = 8;
+constexpr int CONS_THREADS = CONS_WARPS * 32;  // 256: 2 columns each = STRIP_LOAD
+constexpr int STREAM_THREADS = CONS_THREADS + 32;
+constexpr int ROW_BYTES = STRIP_LOAD * 8;  // 4096
+
+struct StageMeta {
+  int col0;    // storage column of the strip's first loaded column
+  int y0;      // grid row of the stage's first row
+  int nrows;   // rows in this stage (<= HS)
+  int flags;   // META_*
+  int ya, yb;  // emit rows of the tile: [ya, yb)
+  int xlo;     // first unknown x in these rows
+  int pad;
+};
+enum { META_TILE_FIRST = 1, META_END = 2 };
+
+// ---------------------------------------------------------------------------------- mbarrier / bulk copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void decode_tile(const Geom& g, int tile, int& strip, int& ya, int& yb, int& xlo) {
+  // block B tiles first, then block U; the strips of one row chunk are adjacent in tile order
+  if (tile < g.tilesB) {
+    const int nsB = g.strips - g.stripB0;
+    const int chunk = tile / nsB;
+    strip = g.stripB0 + (tile - chunk * nsB);
+    ya = g.yB0 + chunk * g.tile_rows;
+    yb = min(ya + g.tile_rows, g.yB1);
+    xlo = g.xsplit + 1;
+  } else {
+    const int t = tile - g.tilesB;
+    const int chunk = t / g.strips;
+    strip = t - chunk * g.strips;
+    ya = g.yU0 + chunk * g.tile_rows;
+    yb = min(ya + g.tile_rows, g.yU1);
+    xlo = 1;
+  }
+}
+
+template <int MODE, int FLAGS>
+struct StreamCfg {
+  static constexpr bool LOAD_R = (MODE != MODE_APPLY) || (FLAGS & (F_SUB_B | F_REPORT));
+  static constexpr bool LOAD_X = (MODE == MODE_UPD);
+  static constexpr bool LOAD_U = (FLAGS & F_U) != 0;
+  static constexpr bool REPORT = (FLAGS & F_REPORT) != 0;
+  static constexpr int NSTREAM = 1 + (LOAD_R ? 1 : 0) + (LOAD_X ? 1 : 0) + (LOAD_U ? 1 : 0);
+  static constexpr int NS = (MODE == MODE_DOT) ? 2 : (MODE == MODE_UPD ? (REPORT ? 3 : 1) : (REPORT ? 2 : 0));
+  static constexpr int NM = (MODE == MODE_UPD) ? (LOAD_U ? 3 : 2) : 0;
+};
+
+template <int MODE, int FLAGS, int HS, int NST>
+constexpr size_t stream_smem_bytes() {
+  return (size_t)NST * HS * StreamCfg<MODE, FLAGS>::NSTREAM * ROW_BYTES + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
+}
+
+template <int MODE, int FLAGS, int HS, int NST>
+__global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const TileArgs a) {
+  using Cfg = StreamCfg<MODE, FLAGS>;
+  constexpr bool LOAD_R = Cfg::LOAD_R, LOAD_X = Cfg::LOAD_X, LOAD_U = Cfg::LOAD_U, REPORT = Cfg::REPORT;
+  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, NM = Cfg::NM;
+  constexpr int STAGE_DOUBLES = HS * NSTREAM * STRIP_LOAD;
+  // stream order inside a stage: p, [r], [x], [u]; each HS rows of STRIP_LOAD doubles
+  constexpr int OFF_P = 0, OFF_R = HS * STRIP_LOAD, OFF_X = (1 + (LOAD_R ? 1 : 0)) * HS * STRIP_LOAD,
+                OFF_U = (1 + (LOAD_R ? 1 : 0) + (LOAD_X ? 1 : 0)) * HS * STRIP_LOAD;
+
+  const Geom& g = a.g;
+  DevState* st = a.st;
+  if (MODE == MODE_APPLY) {
+    if (REPORT && st->report_pending == 0) return;  // no report pending
+  } else {
+    if (st->done) return;
+  }
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage_data = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + NST;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + NST);
+  __shared__ double scratch[(NS + NM > 0 ? NS + NM : 1) * 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double acc_s[NS > 0 ? NS : 1] = {0.0};
+  double acc_m[NM > 0 ? NM : 1] = {0.0};
+
+  if (warp == CONS_WARPS) {
+    // ================================================================ producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t pitch = (size_t)g.pitch;
+      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+        int strip, ya, yb, xlo;
+        decode_tile(g, tile, strip, ya, yb, xlo);
+        const int col0 = strip * STRIP_OUT;
+        const uint32_t row_bytes = (uint32_t)min(STRIP_LOAD, g.pitch - col0) * 8u;
+        const int S = yb - ya + 2;  // rows ya-1 .. yb
+        for (int s0 = 0; s0 < S; s0 += HS) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const int nrows = min(HS, S - s0);
+          const int y0 = ya - 1 + s0;
+          StageMeta m;
+          m.col0 = col0; m.y0 = y0; m.nrows = nrows; m.flags = (s0 == 0) ? META_TILE_FIRST : 0;
+          m.ya = ya; m.yb = yb; m.xlo = xlo; m.pad = 0;
+          meta[stage] = m;
+          // inner rows (emit rows) also need x / u
+          int inner = 0;
+          for (int j = 0; j < nrows; ++j) inner += (y0 + j >= ya && y0 + j < yb) ? 1 : 0;
+          const uint32_t bytes = row_bytes * (uint32_t)(nrows * (1 + (LOAD_R ? 1 : 0)) + inner * ((LOAD_X ? 1 : 0) + (LOAD_U ? 1 : 0)));
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
+          for (int j = 0; j < nrows; ++j) {
+            const int y = y0 + j;
+            const size_t off = (size_t)(y - g.ybase) * pitch + (size_t)col0;
+            bulk_g2s(sd + OFF_P + j * STRIP_LOAD, a.p_in + off, row_bytes, &full[stage]);
+            if (LOAD_R) bulk_g2s(sd + OFF_R + j * STRIP_LOAD, a.r_in + off, row_bytes, &full[stage]);
+            if (y >= ya && y < yb) {
+              if (LOAD_X) bulk_g2s(sd + OFF_X + j * STRIP_LOAD, a.x + off, row_bytes, &full[stage]);
+              if (LOAD_U) bulk_g2s(sd + OFF_U + j * STRIP_LOAD, a.u + off, row_bytes, &full[stage]);
+            }
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+      // end marker
+      mbar_wait(&empty[stage], phase ^ 1u);
+      StageMeta m;
+      m.col0 = 0; m.y0 = 0; m.nrows = 0; m.flags = META_END; m.ya = 0; m.yb = 0; m.xlo = 0; m.pad = 0;
+      meta[stage] = m;
+      mbar_arrive(&full[stage]);
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ consumers
+    const double cA = g.A, cxk = g.xk, cyk = g.yk;
+    double alpha = 0.0, beta = 0.0;
+    if (MODE != MODE_APPLY) {
+      beta = st->beta;
+      if (MODE == MODE_UPD) alpha = st->alpha;
+    }
+    const size_t pitch = (size_t)g.pitch;
+    const bool is_out = (tid >= STRIP_HALO / 2) && (tid < CONS_THREADS - STRIP_HALO / 2);
+    const int c2 = 2 * tid;  // column inside the strip
+
+    int stage = 0;
+    uint32_t phase = 0;
+    // per-tile state
+    bool v0 = false, v1 = false;
+    int ya = 0;
+    size_t eoff = 0;
+    double2 pm = make_double2(0.0, 0.0), pc = make_double2(0.0, 0.0);
+    double2 r_prev = make_double2(0.0, 0.0), x_prev = make_double2(0.0, 0.0), u_prev = make_double2(0.0, 0.0);
+    double Lp = 0.0, Rp = 0.0;
+
+    for (;;) {
+      mbar_wait(&full[stage], phase);
+      const StageMeta m = meta[stage];
+      if (m.flags & META_END) break;
+      if (m.flags & META_TILE_FIRST) {
+        const int x0 = m.col0 + c2 - XOFF;
+        v0 = is_out && (x0 >= m.xlo) && (x0 <= g.n - 1);
+        v1 = is_out && (x0 + 1 >= m.xlo) && (x0 + 1 <= g.n - 1);
+        ya = m.ya;
+        eoff = (size_t)(ya - g.ybase) * pitch + (size_t)(m.col0 + c2);
+        pm = pc = make_double2(0.0, 0.0);
+      }
+      const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
+#pragma unroll
+      for (int j = 0; j < HS; ++j) {
+        if (j >= m.nrows) break;
+        const int y = m.y0 + j;
+        const double* prow = sd + OFF_P + j * STRIP_LOAD;
+        const double* rrow = sd + OFF_R + j * STRIP_LOAD;
+        const double2 cur_p = *reinterpret_cast<const double2*>(prow + c2);
+        double2 cur_r = make_double2(0.0, 0.0), cur_x = make_double2(0.0, 0.0), cur_u = make_double2(0.0, 0.0);
+        if (LOAD_R) cur_r = *reinterpret_cast<const double2*>(rrow + c2);
+        const bool inner = (y >= ya) && (y < m.yb);
+        if (LOAD_X && inner) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + c2);
+        if (LOAD_U && inner) cur_u = *reinterpret_cast<const double2*>(sd + OFF_U + j * STRIP_LOAD + c2);
+        // direction of this row: p = r + beta * p_old (matrix_free_system.cpp:436-438)
+        double2 pn;
+        if (MODE == MODE_APPLY) {
+          pn = cur_p;
+        } else {
+          pn.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
+          pn.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
+        }
+        // horizontal neighbours: shuffle inside the warp, warp-edge lanes recompute from the staged rows
+        double L = __shfl_up_sync(0xffffffffu, pn.y, 1);
+        double R = __shfl_down_sync(0xffffffffu, pn.x, 1);
+        if (lane == 0) {
+          L = 0.0;
+          if (tid > 0) {
+            const double pl = prow[c2 - 1];
+            L = (MODE == MODE_APPLY) ? pl : __dadd_rn(rrow[c2 - 1], __dmul_rn(beta, pl));
+          }
+        }
+        if (lane == 31) {
+          R = 0.0;
+          if (tid < CONS_THREADS - 1) {
+            const double pr = prow[c2 + 2];
+            R = (MODE == MODE_APPLY) ? pr : __dadd_rn(rrow[c2 + 2], __dmul_rn(beta, pr));
+          }
+        }
+
+        if (y > ya) {
+          // emit row y-1: centre pc, bottom pm, top pn; accumulation order diag, left, right, top, bottom
+          // (matrix_free_system.cpp:216-266), each term a rounded multiply then a rounded add.
+          double ap0 = __dmul_rn(cA, pc.x);
+          ap0 = __dadd_rn(ap0, __dmul_rn(cxk, Lp));
+          ap0 = __dadd_rn(ap0, __dmul_rn(cxk, pc.y));
+          ap0 = __dadd_rn(ap0, __dmul_rn(cyk, pn.x));
+          ap0 = __dadd_rn(ap0, __dmul_rn(cyk, pm.x));
+          double ap1 = __dmul_rn(cA, pc.y);
+          ap1 = __dadd_rn(ap1, __dmul_rn(cxk, pc.x));
+          ap1 = __dadd_rn(ap1, __dmul_rn(cxk, Rp));
+          ap1 = __dadd_rn(ap1, __dmul_rn(cyk, pn.y));
+          ap1 = __dadd_rn(ap1, __dmul_rn(cyk, pm.y));
+          const double p0 = v0 ? pc.x : 0.0, p1 = v1 ? pc.y : 0.0;
+          const bool st_ok = v0 || v1;
+          if (MODE == MODE_DOT) {
+            acc_s[0] = fma(p0, ap0, acc_s[0]);
+            acc_s[0] = fma(p1, ap1, acc_s[0]);
+            acc_s[1] = fma(r_prev.x, p0, acc_s[1]);
+            acc_s[1] = fma(r_prev.y, p1, acc_s[1]);
+          } else if (MODE == MODE_UPD) {
+            // x += alpha p; r -= alpha Ap (matrix_free_system.cpp:422-429)
+            double2 xn, rn;
+            xn.x = v0 ? __dadd_rn(x_prev.x, __dmul_rn(alpha, pc.x)) : 0.0;
+            xn.y = v1 ? __dadd_rn(x_prev.y, __dmul_rn(alpha, pc.y)) : 0.0;
+            rn.x = v0 ? __dsub_rn(r_prev.x, __dmul_rn(alpha, ap0)) : 0.0;
+            rn.y = v1 ? __dsub_rn(r_prev.y, __dmul_rn(alpha, ap1)) : 0.0;
+            if (st_ok) {
+              st2(a.x + eoff, xn);
+              st2(a.r_out + eoff, rn);
+              st2(a.p_out + eoff, make_double2(p0, p1));
+            }
+            acc_s[0] = fma(rn.x, rn.x, acc_s[0]);
+            acc_s[0] = fma(rn.y, rn.y, acc_s[0]);
+            acc_m[0] = fmax(acc_m[0], fmax(fabs(rn.x), fabs(rn.y)));
+            const double d0 = v0 ? __dsub_rn(xn.x, x_prev.x) : 0.0;  // msg_solver.cpp:124-129
+            const double d1 = v1 ? __dsub_rn(xn.y, x_prev.y) : 0.0;
+            acc_m[1] = fmax(acc_m[1], fmax(fabs(d0), fabs(d1)));
+            if (REPORT) {
+              acc_s[1] = fma(d0, d0, acc_s[1]);
+              acc_s[1] = fma(d1, d1, acc_s[1]);
+            }
+            if (LOAD_U) {
+              const double e0 = v0 ? __dsub_rn(xn.x, u_prev.x) : 0.0;  // msg_solver.cpp:132-139
+              const double e1 = v1 ? __dsub_rn(xn.y, u_prev.y) : 0.0;
+              acc_m[NM - 1] = fmax(acc_m[NM - 1], fmax(fabs(e0), fabs(e1)));
+              if (REPORT) {
+                acc_s[2] = fma(e0, e0, acc_s[2]);
+                acc_s[2] = fma(e1, e1, acc_s[2]);
+              }
+            }
+          } else {
+            if (REPORT) {
+              const double d0 = v0 ? __dsub_rn(r_prev.x, ap0) : 0.0;  // b - A x, matrix_free_system.cpp:459-463
+              const double d1 = v1 ? __dsub_rn(r_prev.y, ap1) : 0.0;
+              acc_s[0] = fma(d0, d0, acc_s[0]);
+              acc_s[0] = fma(d1, d1, acc_s[0]);
+              if (LOAD_U) {
+                const double e0 = v0 ? __dsub_rn(pc.x, u_prev.x) : 0.0;
+                const double e1 = v1 ? __dsub_rn(pc.y, u_prev.y) : 0.0;
+                acc_s[1] = fma(e0, e0, acc_s[1]);
+                acc_s[1] = fma(e1, e1, acc_s[1]);
+              }
+            } else if (st_ok) {
+              double2 o;
+              if (FLAGS & F_SUB_B) {
+                o.x = v0 ? __dsub_rn(ap0, r_prev.x) : 0.0;  // A x - b, dirichlet_solver.cpp:156-158
+                o.y = v1 ? __dsub_rn(ap1, r_prev.y) : 0.0;
+              } else {
+                o.x = v0 ? ap0 : 0.0;
+                o.y = v1 ? ap1 : 0.0;
+              }
+              st2(a.out + eoff, o);
+            }
+          }
+          eoff += pitch;
+        }
+        pm = pc;
+        pc = pn;
+        Lp = L;
+        Rp = R;
+        r_prev = cur_r;
+        x_prev = cur_x;
+        u_prev = cur_u;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  if (NS + NM == 0) return;
+  if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
+  // ---- one thread: turn the totals into the next scalars
+  if (a.defer) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st->loc_s[k] = k < NS ? acc_s[k < NS ? k : 0] : 0.0;
+      st->loc_m[k] = k < NM ? acc_m[k < NM ? k : 0] : 0.0;
+    }
+    return;
+  }
+  if (MODE == MODE_DOT) {
+    finalize_dot(st, acc_s[0], acc_s[1]);
+  } else if (MODE == MODE_UPD) {
+    finalize_update(st, a.cb_log, acc_s[0], acc_m[0], acc_m[1], LOAD_U ? acc_m[NM - 1] : DBL_MAX,
+                    REPORT ? acc_s[1] : 0.0, (REPORT && LOAD_U) ? acc_s[2] : 0.0, REPORT);
+  } else if (REPORT) {
+    finalize_report(st, a.cb_log, acc_s[0], LOAD_U ? acc_s[1] : 0.0, LOAD_U);
+  }
+}
+
+}  // namespace b200cg
