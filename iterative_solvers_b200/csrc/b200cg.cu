@@ -61,6 +61,9 @@ struct b200cg_plan_s {
   Geom g;
   int sms = 148;
   int ctas_per_sm = 2;  // resident CTAs of the persistent sweep kernel per SM
+  Tile* d_tiles = nullptr;
+  int* d_cta_begin = nullptr;
+  int sweep_grid = 0, n_tiles = 0;
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
   double* r[2] = {nullptr, nullptr};
@@ -157,19 +160,67 @@ static int setup_geometry(b200cg_plan_s* P) {
   g.hi = (g.yhi >= d.m) ? P->n_global : row_start(g, g.yhi);
   g.pitch = ((d.n + 1 + XOFF) + 15) / 16 * 16;
 
-  g.tile_rows = d.tile_rows > 0 ? d.tile_rows : 64;
-  g.strips = (d.n - 1) / STRIP_OUT + 1;
-  g.stripB0 = (g.xsplit + 1) / STRIP_OUT;
-  g.yB0 = g.ylo;
-  g.yB1 = std::max(g.ylo, std::min(g.yhi, g.ysplit + 1));
-  g.yU0 = std::max(g.ylo, g.ysplit + 1);
-  g.yU1 = std::max(g.yU0, g.yhi);
-  if (g.ysplit == 0) g.yB1 = g.yB0;
-  g.chunksB = (g.yB1 - g.yB0 + g.tile_rows - 1) / g.tile_rows;
-  g.chunksU = (g.yU1 - g.yU0 + g.tile_rows - 1) / g.tile_rows;
-  g.tilesB = g.chunksB * (g.strips - g.stripB0);
-  g.tiles = g.tilesB + g.chunksU * g.strips;
   return B200CG_OK;
+}
+
+// Cuts the sweep over this rank's rows into tiles and deals them to the resident CTAs.
+// Default policy: linearise all (strip, row) pairs strip-major, cut the sequence into grid * TILES_PER_CTA
+// equal ranges (split where a range crosses a strip end) and give CTA c the ranges c, c + grid, ... - every
+// CTA gets the same number of rows to within one, and a tile's two halo rows are amortised over its height.
+// desc.tile_rows > 0 forces fixed-height tiles instead (tests: ragged heights, many tiles per CTA).
+static void build_tiles(b200cg_plan_s* P, std::vector<Tile>* tiles, std::vector<int>* cta_begin, int* grid_out) {
+  const Geom& g = P->g;
+  struct Col { int col0, y0, y1, xlo; };
+  std::vector<Col> cols;  // one entry per (block, strip)
+  const int strips = (g.n - 1) / STRIP_OUT + 1;
+  const int yB0 = g.ylo, yB1 = g.ysplit ? std::max(g.ylo, std::min(g.yhi, g.ysplit + 1)) : g.ylo;
+  const int yU0 = std::max(g.ylo, g.ysplit + 1), yU1 = std::max(yU0, g.yhi);
+  if (yB1 > yB0)
+    for (int s = (g.xsplit + 1) / STRIP_OUT; s < strips; ++s) cols.push_back({s * STRIP_OUT, yB0, yB1, g.xsplit + 1});
+  if (yU1 > yU0)
+    for (int s = 0; s < strips; ++s) cols.push_back({s * STRIP_OUT, yU0, yU1, 1});
+  long long total = 0;
+  for (const Col& c : cols) total += c.y1 - c.y0;
+  const int max_grid = P->sms * P->ctas_per_sm;
+  std::vector<std::vector<Tile>> per_cta;
+  if (P->desc.tile_rows > 0) {
+    std::vector<Tile> all;
+    for (const Col& c : cols)
+      for (int y = c.y0; y < c.y1; y += P->desc.tile_rows)
+        all.push_back({c.col0, y, std::min(y + P->desc.tile_rows, c.y1), c.xlo});
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(all.size(), (size_t)max_grid));
+    per_cta.resize(grid);
+    for (size_t i = 0; i < all.size(); ++i) per_cta[i % grid].push_back(all[i]);
+  } else {
+    const int MIN_ROWS = 4;       // below this the two halo rows dominate
+    const int TILES_PER_CTA = 4;  // ranges per CTA when there is enough work
+    long long nranges = std::min<long long>((long long)max_grid * TILES_PER_CTA, std::max<long long>(1, total / MIN_ROWS));
+    int grid = (int)std::min<long long>(max_grid, nranges);
+    if (nranges > grid) nranges = (nranges / grid) * grid;  // same count for every CTA
+    per_cta.resize(std::max(grid, 1));
+    size_t ci = 0;
+    long long pos = 0;  // linear position of cols[ci].y0
+    for (long long r = 0; r < nranges; ++r) {
+      long long lo = total * r / nranges, hi = total * (r + 1) / nranges;
+      while (lo < hi) {
+        while (ci < cols.size() && pos + (cols[ci].y1 - cols[ci].y0) <= lo) {
+          pos += cols[ci].y1 - cols[ci].y0;
+          ++ci;
+        }
+        const Col& c = cols[ci];
+        const long long seg_hi = std::min<long long>(hi, pos + (c.y1 - c.y0));
+        per_cta[r % per_cta.size()].push_back({c.col0, (int)(c.y0 + (lo - pos)), (int)(c.y0 + (seg_hi - pos)), c.xlo});
+        lo = seg_hi;
+      }
+    }
+  }
+  tiles->clear();
+  cta_begin->assign(1, 0);
+  for (const auto& v : per_cta) {
+    tiles->insert(tiles->end(), v.begin(), v.end());
+    cta_begin->push_back((int)tiles->size());
+  }
+  *grid_out = (int)per_cta.size();
 }
 
 static int ew_grid(const b200cg_plan_s* P, long long work_items) {
@@ -232,6 +283,8 @@ static void free_plan(b200cg_plan_s* P) {
   cudaFree(P->d_state);
   cudaFree(P->d_log);
   cudaFree(P->d_partials);
+  cudaFree(P->d_tiles);
+  cudaFree(P->d_cta_begin);
   if (P->h_state) cudaFreeHost(P->h_state);
   if (P->h_log) cudaFreeHost(P->h_log);
   for (auto& e : P->ev)
@@ -277,7 +330,17 @@ static int plan_create_impl(b200cg_plan_s* P) {
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
-  P->partial_slots = std::max(g.tiles, P->sms * 16) + 64;
+  {
+    std::vector<Tile> tiles;
+    std::vector<int> cta_begin;
+    build_tiles(P, &tiles, &cta_begin, &P->sweep_grid);
+    P->n_tiles = (int)tiles.size();
+    CU(cudaMalloc(&P->d_tiles, std::max<size_t>(tiles.size(), 1) * sizeof(Tile)));
+    CU(cudaMalloc(&P->d_cta_begin, cta_begin.size() * sizeof(int)));
+    if (!tiles.empty()) CU(cudaMemcpy(P->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(P->d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  P->partial_slots = P->sms * 16 + 64;
   CU(cudaMalloc(&P->d_partials, sizeof(double) * MAX_PARTIALS * (size_t)P->partial_slots));
   if (P->desc.world > 1) {
     std::string err;
@@ -434,7 +497,7 @@ struct StreamShape {
 
 template <int MODE, int FLAGS>
 static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (P->g.tiles <= 0) return B200CG_OK;
+  if (P->n_tiles <= 0) return B200CG_OK;
   using Sh = StreamShape<MODE, FLAGS>;
   auto kernel = cg_stream_kernel<MODE, FLAGS, Sh::HS, Sh::NST>;
   constexpr size_t smem = stream_smem_bytes<MODE, FLAGS, Sh::HS, Sh::NST>();
@@ -444,8 +507,7 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = true;
   }
-  const int grid = std::min(P->g.tiles, P->sms * P->ctas_per_sm);
-  kernel<<<grid, STREAM_THREADS, smem, s>>>(a);
+  kernel<<<P->sweep_grid, STREAM_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
 }
@@ -456,6 +518,8 @@ static TileArgs base_args(b200cg_plan_s* P) {
   a.st = P->d_state;
   a.partials = P->d_partials;
   a.cb_log = P->d_log;
+  a.tiles = P->d_tiles;
+  a.cta_begin = P->d_cta_begin;
   a.defer = P->desc.world > 1 ? 1 : 0;
   a.g = P->g;
   return a;

@@ -28,18 +28,18 @@ struct Geom {
   int ylo, yhi;        // unknown rows owned by this rank: [ylo, yhi) within [1, m)
   double A, xk, yk;    // -2(xk+yk), 1/hx^2, 1/hy^2 (grid_system.cpp:316-318)
   double a, c, hx, hy; // node coordinates x = a + i*hx, y = c + j*hy
-  // tiling
-  int tile_rows;       // rows per tile
-  int strips;          // strips covering x in [0, n-1]
-  int stripB0;         // first strip that intersects block B columns (x > xsplit)
-  int yB0, yB1;        // local rows of block B: [yB0, yB1)   (y <= ysplit)
-  int yU0, yU1;        // local rows of block U: [yU0, yU1)   (y >  ysplit)
-  int chunksB, chunksU;
-  int tilesB, tiles;   // tilesB = chunksB * (strips - stripB0); tiles = tilesB + chunksU * strips
   // compact (reference) ordering
   long long NB;        // unknowns in block B (global)
   int wB, wU;          // row widths of block B / block U (RECT: wB unused, wU = n-1)
   long long lo, hi;    // compact index range owned by this rank
+};
+
+// One unit of sweep work: rows [ya, yb) of one 512-column strip. The host cuts the sweep into equal-work tiles
+// and deals them to the resident CTAs (b200cg.cu: build_tiles); the producer warp just walks its list.
+struct Tile {
+  int col0;  // storage column of the first loaded column (strip * STRIP_OUT)
+  int ya, yb;
+  int xlo;   // first unknown x in these rows (1, or xsplit+1 in block B)
 };
 
 // Scalars of the iteration live on the device; the host never sees alpha/beta.

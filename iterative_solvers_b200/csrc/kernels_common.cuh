@@ -32,6 +32,8 @@ struct TileArgs {
   DevState* st;
   double* partials;    // [MAX_PARTIALS][gridDim.x]
   CbRecord* cb_log;
+  const Tile* tiles;      // tile table, grouped per CTA
+  const int* cta_begin;   // [gridDim.x + 1] offsets into tiles
   int defer;           // sharded plan: publish this rank's totals in st->loc_*, finalize after the all-reduce
   Geom g;
 };

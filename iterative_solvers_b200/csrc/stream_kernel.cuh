@@ -9,7 +9,7 @@
 //                   Warps only meet at the stage mbarriers - there is no per-row __syncthreads.
 // A strip loads 4 extra columns on each side (one 32-byte sector), so every output column finds its
 // neighbours inside the CTA. Stage metadata written by the producer tells consumers what a stage holds, so the
-// tile order is the producer's business alone (static round-robin over a grid of resident CTAs).
+// tile order is the producer's business alone: it walks the list of equal-work tiles the host dealt to this CTA.
 #pragma once
 #include <cuda/std/cstdint>
 #include "kernels_common.cuh"
@@ -64,25 +64,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-__device__ __forceinline__ void decode_tile(const Geom& g, int tile, int& strip, int& ya, int& yb, int& xlo) {
-  // block B tiles first, then block U; the strips of one row chunk are adjacent in tile order
-  if (tile < g.tilesB) {
-    const int nsB = g.strips - g.stripB0;
-    const int chunk = tile / nsB;
-    strip = g.stripB0 + (tile - chunk * nsB);
-    ya = g.yB0 + chunk * g.tile_rows;
-    yb = min(ya + g.tile_rows, g.yB1);
-    xlo = g.xsplit + 1;
-  } else {
-    const int t = tile - g.tilesB;
-    const int chunk = t / g.strips;
-    strip = t - chunk * g.strips;
-    ya = g.yU0 + chunk * g.tile_rows;
-    yb = min(ya + g.tile_rows, g.yU1);
-    xlo = 1;
-  }
 }
 
 template <int MODE, int FLAGS>
@@ -145,10 +126,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
       int stage = 0;
       uint32_t phase = 0;
       const size_t pitch = (size_t)g.pitch;
-      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-        int strip, ya, yb, xlo;
-        decode_tile(g, tile, strip, ya, yb, xlo);
-        const int col0 = strip * STRIP_OUT;
+      const int t_end = a.cta_begin[blockIdx.x + 1];
+      for (int t = a.cta_begin[blockIdx.x]; t < t_end; ++t) {
+        const Tile tl = a.tiles[t];
+        const int col0 = tl.col0, ya = tl.ya, yb = tl.yb, xlo = tl.xlo;
         const uint32_t row_bytes = (uint32_t)min(STRIP_LOAD, g.pitch - col0) * 8u;
         const int S = yb - ya + 2;  // rows ya-1 .. yb
         for (int s0 = 0; s0 < S; s0 += HS) {
@@ -272,20 +253,26 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
           ap1 = __dadd_rn(ap1, __dmul_rn(cxk, Rp));
           ap1 = __dadd_rn(ap1, __dmul_rn(cyk, pn.y));
           ap1 = __dadd_rn(ap1, __dmul_rn(cyk, pm.y));
+          // Columns that are not unknowns of this tile (boundary, excluded quadrant, halo columns, columns past
+          // the row pitch whose staged values are stale) contribute exact zeros: mask every operand once.
+          ap0 = v0 ? ap0 : 0.0;
+          ap1 = v1 ? ap1 : 0.0;
           const double p0 = v0 ? pc.x : 0.0, p1 = v1 ? pc.y : 0.0;
+          const double r0 = v0 ? r_prev.x : 0.0, r1 = v1 ? r_prev.y : 0.0;
           const bool st_ok = v0 || v1;
           if (MODE == MODE_DOT) {
             acc_s[0] = fma(p0, ap0, acc_s[0]);
             acc_s[0] = fma(p1, ap1, acc_s[0]);
-            acc_s[1] = fma(r_prev.x, p0, acc_s[1]);
-            acc_s[1] = fma(r_prev.y, p1, acc_s[1]);
+            acc_s[1] = fma(r0, p0, acc_s[1]);
+            acc_s[1] = fma(r1, p1, acc_s[1]);
           } else if (MODE == MODE_UPD) {
             // x += alpha p; r -= alpha Ap (matrix_free_system.cpp:422-429)
+            const double xo0 = v0 ? x_prev.x : 0.0, xo1 = v1 ? x_prev.y : 0.0;
             double2 xn, rn;
-            xn.x = v0 ? __dadd_rn(x_prev.x, __dmul_rn(alpha, pc.x)) : 0.0;
-            xn.y = v1 ? __dadd_rn(x_prev.y, __dmul_rn(alpha, pc.y)) : 0.0;
-            rn.x = v0 ? __dsub_rn(r_prev.x, __dmul_rn(alpha, ap0)) : 0.0;
-            rn.y = v1 ? __dsub_rn(r_prev.y, __dmul_rn(alpha, ap1)) : 0.0;
+            xn.x = __dadd_rn(xo0, __dmul_rn(alpha, p0));
+            xn.y = __dadd_rn(xo1, __dmul_rn(alpha, p1));
+            rn.x = __dsub_rn(r0, __dmul_rn(alpha, ap0));
+            rn.y = __dsub_rn(r1, __dmul_rn(alpha, ap1));
             if (st_ok) {
               st2(a.x + eoff, xn);
               st2(a.r_out + eoff, rn);
@@ -294,8 +281,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
             acc_s[0] = fma(rn.x, rn.x, acc_s[0]);
             acc_s[0] = fma(rn.y, rn.y, acc_s[0]);
             acc_m[0] = fmax(acc_m[0], fmax(fabs(rn.x), fabs(rn.y)));
-            const double d0 = v0 ? __dsub_rn(xn.x, x_prev.x) : 0.0;  // msg_solver.cpp:124-129
-            const double d1 = v1 ? __dsub_rn(xn.y, x_prev.y) : 0.0;
+            const double d0 = __dsub_rn(xn.x, xo0);  // msg_solver.cpp:124-129
+            const double d1 = __dsub_rn(xn.y, xo1);
             acc_m[1] = fmax(acc_m[1], fmax(fabs(d0), fabs(d1)));
             if (REPORT) {
               acc_s[1] = fma(d0, d0, acc_s[1]);
@@ -312,8 +299,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
             }
           } else {
             if (REPORT) {
-              const double d0 = v0 ? __dsub_rn(r_prev.x, ap0) : 0.0;  // b - A x, matrix_free_system.cpp:459-463
-              const double d1 = v1 ? __dsub_rn(r_prev.y, ap1) : 0.0;
+              const double d0 = __dsub_rn(r0, ap0);  // b - A x, matrix_free_system.cpp:459-463
+              const double d1 = __dsub_rn(r1, ap1);
               acc_s[0] = fma(d0, d0, acc_s[0]);
               acc_s[0] = fma(d1, d1, acc_s[0]);
               if (LOAD_U) {
@@ -325,11 +312,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
             } else if (st_ok) {
               double2 o;
               if (FLAGS & F_SUB_B) {
-                o.x = v0 ? __dsub_rn(ap0, r_prev.x) : 0.0;  // A x - b, dirichlet_solver.cpp:156-158
-                o.y = v1 ? __dsub_rn(ap1, r_prev.y) : 0.0;
+                o.x = __dsub_rn(ap0, r0);  // A x - b, dirichlet_solver.cpp:156-158
+                o.y = __dsub_rn(ap1, r1);
               } else {
-                o.x = v0 ? ap0 : 0.0;
-                o.y = v1 ? ap1 : 0.0;
+                o.x = ap0;
+                o.y = ap1;
               }
               st2(a.out + eoff, o);
             }

@@ -53,6 +53,9 @@ typedef struct {
 void cgo_mf_solve(const cgo_grid* g, const double* b, const double* u, double eps, int max_it, double* x,
                   cgo_mf_info* info, double* hist, int hist_cap, double* snapshot_r, double* snapshot_p);
 
+/* 0 = reference summation order (default), 1 = long-double accumulation (diagnostic, see cg_oracle.c) */
+void cgo_set_dot_mode(int mode);
+
 long cgo_csr_nnz(const cgo_grid* g);
 /* GridSystem::initiate_matrix (grid_system.cpp:157-274): per row diag, left, right, top, bottom. */
 void cgo_csr_assemble(const cgo_grid* g, int* row_map, int* entries, double* values);

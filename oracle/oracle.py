@@ -110,7 +110,15 @@ class Oracle:
         self.L.cgo_apply(C.byref(self.g), _opt(x), _opt(y))
         return y
 
-    def mf_solve(self, b=None, eps=1e-6, max_it=10000, with_hist=False, snapshots=False):
+    def mf_solve(self, b=None, eps=1e-6, max_it=10000, with_hist=False, snapshots=False, accurate_dots=False):
+        """accurate_dots=True: diagnostic long-double summation instead of the reference's sequential fp64."""
+        self.L.cgo_set_dot_mode(1 if accurate_dots else 0)
+        try:
+            return self._mf_solve(b, eps, max_it, with_hist, snapshots)
+        finally:
+            self.L.cgo_set_dot_mode(0)
+
+    def _mf_solve(self, b, eps, max_it, with_hist, snapshots):
         b = self.rhs() if b is None else np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty(self.N)
         info = MfInfo()

