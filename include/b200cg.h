@@ -39,7 +39,9 @@ typedef enum {
   B200CG_DOMAIN_LSHAPE = 0, /* the reference's L-shaped region: rectangle minus its lower-left quadrant
                                (grid_system.cpp:17-43); requires even n == m (the reference numbering is
                                only self-consistent there, grid_system.cpp:103-111) */
-  B200CG_DOMAIN_RECT = 1    /* full rectangle, any n, m >= 2 (no reference counterpart; synthetic configs) */
+  B200CG_DOMAIN_RECT = 1,   /* full rectangle, any n, m >= 2 (no reference counterpart; synthetic configs) */
+  B200CG_DOMAIN_GENERIC = 2 /* no geometry: a plan of generic_rows unknowns that only serves the CSR entry points
+                               (MSGSolver receives just a matrix and a rhs, msg_solver.hpp:50-53) */
 } b200cg_domain;
 
 typedef enum {
@@ -76,7 +78,9 @@ typedef struct {
   int rank, world;       /* row-slab sharding, one process per GPU; world <= 1: single GPU */
   const void* comm_id;   /* world > 1: the 128-byte id from b200cg_comm_unique_id() of rank 0 */
   int tile_rows;         /* rows a CTA marches per tile; 0 = default */
-  int reserved[7];
+  int reserved0;
+  int64_t generic_rows;  /* B200CG_DOMAIN_GENERIC: number of unknowns (n, m, a..d are ignored) */
+  int reserved[4];
 } b200cg_plan_desc;
 
 typedef struct {

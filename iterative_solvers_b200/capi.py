@@ -9,7 +9,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200CG_LIB", os.path.join(PKG, "libb200cg.so"))
 
-DOMAIN_LSHAPE, DOMAIN_RECT = 0, 1
+DOMAIN_LSHAPE, DOMAIN_RECT, DOMAIN_GENERIC = 0, 1, 2
 OP_MATRIX_FREE, OP_CSR = 0, 1
 RULE_REL_L2, RULE_MAXNORM = 0, 1
 STOP_NAMES = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]
@@ -35,7 +35,8 @@ class B200CGError(RuntimeError):
 class PlanDesc(C.Structure):
     _fields_ = [("n", C.c_int), ("m", C.c_int), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
                 ("d", C.c_double), ("domain", C.c_int), ("device", C.c_int), ("rank", C.c_int),
-                ("world", C.c_int), ("comm_id", C.c_void_p), ("tile_rows", C.c_int), ("reserved", C.c_int * 7)]
+                ("world", C.c_int), ("comm_id", C.c_void_p), ("tile_rows", C.c_int), ("reserved0", C.c_int),
+                ("generic_rows", C.c_int64), ("reserved", C.c_int * 4)]
 
 
 class Params(C.Structure):
@@ -153,13 +154,14 @@ class Plan:
     """b200cg_plan_t. Constructor arguments follow GridSystem / MatrixFreeSystem: (m, n, a, b, c, d)."""
 
     def __init__(self, m, n, a=0.0, b=1.0, c=0.0, d=1.0, domain=DOMAIN_LSHAPE, device=0, rank=0, world=1,
-                 comm_id: bytes | None = None, tile_rows=0):
+                 comm_id: bytes | None = None, tile_rows=0, generic_rows=0):
         self.L = lib()
         self.h = C.c_void_p()
         self._id = C.create_string_buffer(comm_id, 128) if comm_id else None
         desc = PlanDesc(n=int(n), m=int(m), a=a, b=b, c=c, d=d, domain=int(domain), device=int(device),
                         rank=int(rank), world=int(world),
-                        comm_id=C.cast(self._id, C.c_void_p) if self._id else None, tile_rows=int(tile_rows))
+                        comm_id=C.cast(self._id, C.c_void_p) if self._id else None, tile_rows=int(tile_rows),
+                        generic_rows=int(generic_rows))
         check(self.L.b200cg_plan_create(C.byref(self.h), C.byref(desc)))
         nn = C.c_int64()
         check(self.L.b200cg_size(self.h, C.byref(nn)))

@@ -82,6 +82,8 @@ struct b200cg_plan_s {
   int partial_slots = 0;
   cudaEvent_t ev[8] = {};
   bool have_rhs = false, have_u = false, have_solution = false;
+  bool generic = false;          // B200CG_DOMAIN_GENERIC: CSR entry points only, no pitched vectors
+  bool solution_in_csr = false;  // the last solve ran on the assembled path
   std::map<int, GraphEntry> graphs;
   CsrData csr;
   Comm comm;
@@ -98,6 +100,16 @@ static int setup_geometry(b200cg_plan_s* P) {
   const b200cg_plan_desc& d = P->desc;
   Geom& g = P->g;
   memset(&g, 0, sizeof(g));
+  if (d.domain == B200CG_DOMAIN_GENERIC) {
+    if (d.generic_rows <= 0 || d.generic_rows > 2147483647LL)
+      return fail(B200CG_ERR_INVALID_ARG, "generic plan needs 0 < generic_rows < 2^31 (int32 CSR indices)");
+    if (d.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
+    P->n_global = d.generic_rows;
+    g.lo = 0;
+    g.hi = d.generic_rows;
+    P->ycuts.assign(2, 0);
+    return B200CG_OK;
+  }
   if (d.domain == B200CG_DOMAIN_LSHAPE) {
     if (d.n != d.m || (d.n % 2) != 0 || d.n < 4)
       return fail(B200CG_ERR_INVALID_ARG,
@@ -300,12 +312,12 @@ static int alloc_vec(b200cg_plan_s* P, double** v) {
 }
 
 static int plan_create_impl(b200cg_plan_s* P) {
+  RET(setup_geometry(P));  // argument errors first: they are reported even on a machine without a GPU
   int ndev = 0;
   RET(b200cg_device_count(&ndev));
   if (ndev <= 0) return fail(B200CG_ERR_NO_DEVICE, "no CUDA device visible: libb200cg has no CPU fallback");
   if (P->desc.device < 0 || P->desc.device >= ndev)
     return fail(B200CG_ERR_INVALID_ARG, "device %d outside [0, %d)", P->desc.device, ndev);
-  RET(setup_geometry(P));
   CU(cudaSetDevice(P->desc.device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, P->desc.device));
@@ -316,21 +328,24 @@ static int plan_create_impl(b200cg_plan_s* P) {
   CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   for (auto& e : P->ev) CU(cudaEventCreate(&e));
   const Geom& g = P->g;
-  P->vec_elems = (size_t)g.yrows * (size_t)g.pitch;
-  for (int i = 0; i < 2; ++i) {
-    RET(alloc_vec(P, &P->r[i]));
-    RET(alloc_vec(P, &P->p[i]));
+  P->generic = P->desc.domain == B200CG_DOMAIN_GENERIC;
+  if (!P->generic) {
+    P->vec_elems = (size_t)g.yrows * (size_t)g.pitch;
+    for (int i = 0; i < 2; ++i) {
+      RET(alloc_vec(P, &P->r[i]));
+      RET(alloc_vec(P, &P->p[i]));
+    }
+    RET(alloc_vec(P, &P->x));
+    RET(alloc_vec(P, &P->b));
+    CU(cudaMalloc(&P->compact, std::max<long long>(g.hi - g.lo, 1) * sizeof(double)));
   }
-  RET(alloc_vec(P, &P->x));
-  RET(alloc_vec(P, &P->b));
-  CU(cudaMalloc(&P->compact, std::max<long long>(g.hi - g.lo, 1) * sizeof(double)));
   CU(cudaMalloc(&P->d_state, sizeof(DevState)));
   CU(cudaMemsetAsync(P->d_state, 0, sizeof(DevState), P->stream));
   CU(cudaHostAlloc(&P->h_state, sizeof(DevState), cudaHostAllocDefault));
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
-  {
+  if (!P->generic) {
     std::vector<Tile> tiles;
     std::vector<int> cta_begin;
     build_tiles(P, &tiles, &cta_begin, &P->sweep_grid);
@@ -440,8 +455,15 @@ static int exchange_halo(b200cg_plan_s* P, double* v) {
   return B200CG_OK;
 }
 
+#define NEED_GEOMETRY(P)                                                                                      \
+  do {                                                                                                        \
+    if ((P)->generic)                                                                                         \
+      return fail(B200CG_ERR_UNSUPPORTED, "%s needs a geometric plan (this one is B200CG_DOMAIN_GENERIC)", __func__); \
+  } while (0)
+
 extern "C" int b200cg_build_rhs(b200cg_plan_t P) {
   if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  NEED_GEOMETRY(P);
   CU(cudaSetDevice(P->desc.device));
   setup_kernel<<<ew_grid(P, local_count(P)), CTA_THREADS, 0, P->stream>>>(P->b, nullptr, P->g, 0);
   CU(cudaGetLastError());
@@ -451,6 +473,7 @@ extern "C" int b200cg_build_rhs(b200cg_plan_t P) {
 }
 extern "C" int b200cg_set_rhs(b200cg_plan_t P, const double* b_host) {
   if (!P || !b_host) return fail(B200CG_ERR_INVALID_ARG, "plan/b_host is NULL");
+  NEED_GEOMETRY(P);
   CU(cudaSetDevice(P->desc.device));
   RET(upload_vector(P, b_host, P->b));
   CU(cudaStreamSynchronize(P->stream));
@@ -459,6 +482,7 @@ extern "C" int b200cg_set_rhs(b200cg_plan_t P, const double* b_host) {
 }
 extern "C" int b200cg_get_rhs(b200cg_plan_t P, double* b_host) {
   if (!P || !b_host) return fail(B200CG_ERR_INVALID_ARG, "plan/b_host is NULL");
+  NEED_GEOMETRY(P);
   if (!P->have_rhs) return fail(B200CG_ERR_STATE, "no rhs in the plan: call b200cg_build_rhs or b200cg_set_rhs first");
   CU(cudaSetDevice(P->desc.device));
   RET(download_vector(P, P->b, b_host));
@@ -475,11 +499,13 @@ static int setup_to_host(b200cg_plan_s* P, int what, double* host) {
 }
 extern "C" int b200cg_get_true_solution(b200cg_plan_t P, double* u_host) {
   if (!P || !u_host) return fail(B200CG_ERR_INVALID_ARG, "plan/u_host is NULL");
+  NEED_GEOMETRY(P);
   CU(cudaSetDevice(P->desc.device));
   return setup_to_host(P, 1, u_host);
 }
 extern "C" int b200cg_get_coords(b200cg_plan_t P, double* xs, double* ys) {
   if (!P || !xs || !ys) return fail(B200CG_ERR_INVALID_ARG, "plan/xs/ys is NULL");
+  NEED_GEOMETRY(P);
   CU(cudaSetDevice(P->desc.device));
   RET(setup_to_host(P, 2, xs));
   return setup_to_host(P, 3, ys);
@@ -538,6 +564,7 @@ static int reduce_and_finalize(b200cg_plan_s* P, int which, int flags, bool with
 
 extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_host) {
   if (!P || !x_host || !y_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host/y_host is NULL");
+  NEED_GEOMETRY(P);
   CU(cudaSetDevice(P->desc.device));
   RET(ensure_scratch(P));
   RET(upload_vector(P, x_host, P->va));
@@ -565,6 +592,7 @@ extern "C" int b200cg_set_csr(b200cg_plan_t P, int64_t nrows, int64_t nnz, const
 }
 extern "C" int b200cg_assemble_csr(b200cg_plan_t P, int64_t* nnz) {
   if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  NEED_GEOMETRY(P);
   if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
   CU(cudaSetDevice(P->desc.device));
   std::string err;
@@ -709,6 +737,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   if (prm->rhs_on_device && !P->have_rhs) return fail(B200CG_ERR_STATE, "rhs_on_device set but the plan holds no rhs");
   if (!prm->keep_x_on_device && !x_host) return fail(B200CG_ERR_INVALID_ARG, "x_host is NULL and keep_x_on_device is 0");
   const bool csr = prm->op == B200CG_OP_CSR;
+  if (!csr) NEED_GEOMETRY(P);
   if (csr && !P->csr.row_map) return fail(B200CG_ERR_STATE, "CSR solve without a matrix: call b200cg_set_csr / b200cg_assemble_csr");
   if (csr && prm->rule == B200CG_RULE_REL_L2 && cb) return fail(B200CG_ERR_UNSUPPORTED, "per-iteration report callbacks exist only on the matrix-free path");
   memset(info, 0, sizeof(*info));
@@ -721,18 +750,37 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
 
   // ---- inputs
   CU(cudaEventRecord(P->ev[3], s));
-  if (!prm->rhs_on_device) {
-    RET(upload_vector(P, b_host, P->b));
-    P->have_rhs = true;
-    info->h2d_bytes += cnt * (int64_t)sizeof(double);
-    info->kernel_launches += 1;
-  }
   const bool with_u = (u_host != nullptr);
-  if (with_u) {
-    RET(ensure_u(P));
-    RET(upload_vector(P, u_host, P->u));
-    info->h2d_bytes += cnt * (int64_t)sizeof(double);
-    info->kernel_launches += 1;
+  if (csr) {
+    // the assembled path works on compact vectors: host data goes straight into them
+    std::string err;
+    int rc = csr_ensure_vectors(&P->csr, s, &err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if (!prm->rhs_on_device) {
+      CU(cudaMemcpyAsync(P->csr.b, b_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    } else {
+      gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
+      info->kernel_launches += 1;
+    }
+    if (with_u) {
+      CU(cudaMemcpyAsync(P->csr.u, u_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    }
+    P->csr.has_u = with_u;
+  } else {
+    if (!prm->rhs_on_device) {
+      RET(upload_vector(P, b_host, P->b));
+      P->have_rhs = true;
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+      info->kernel_launches += 1;
+    }
+    if (with_u) {
+      RET(ensure_u(P));
+      RET(upload_vector(P, u_host, P->u));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+      info->kernel_launches += 1;
+    }
   }
   P->have_u = with_u;
   CU(cudaEventRecord(P->ev[4], s));
@@ -753,16 +801,9 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
 
   if (csr) {
-    std::string err;
-    int rc = csr_ensure_vectors(&P->csr, s, &err);
-    if (rc) return fail(rc, "%s", err.c_str());
-    // the assembled path works on compact vectors: gather b (and u) out of the pitched copies
-    gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
-    if (with_u) gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->u, P->csr.u, P->g);
-    P->csr.has_u = with_u;
     csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
     CU(cudaGetLastError());
-    info->kernel_launches += 2 + (with_u ? 1 : 0);
+    info->kernel_launches += 1;
   } else {
     const Geom& g = P->g;
     InitArgs ia;
@@ -845,15 +886,15 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
 
   // ---- outputs
   const DevState st = *P->h_state;
-  if (csr) {
-    // scatter the compact solution into the pitched x so that postprocess / get_solution see one layout
-    scatter_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->csr.x, P->x, P->g);
-    info->kernel_launches += 1;
-  }
+  P->solution_in_csr = csr;
   if (!prm->keep_x_on_device) {
-    RET(download_vector(P, P->x, x_host));
+    if (csr) {
+      CU(cudaMemcpyAsync(x_host, P->csr.x, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      RET(download_vector(P, P->x, x_host));
+      info->kernel_launches += 1;
+    }
     info->d2h_bytes += cnt * (int64_t)sizeof(double);
-    info->kernel_launches += 1;
   }
   CU(cudaEventRecord(P->ev[7], s));
   CU(cudaStreamSynchronize(s));
@@ -889,7 +930,10 @@ extern "C" int b200cg_get_solution(b200cg_plan_t P, double* x_host) {
   if (!P || !x_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host is NULL");
   if (!P->have_solution) return fail(B200CG_ERR_STATE, "no solution in the plan: call b200cg_solve first");
   CU(cudaSetDevice(P->desc.device));
-  RET(download_vector(P, P->x, x_host));
+  if (P->solution_in_csr)
+    CU(cudaMemcpyAsync(x_host, P->csr.x, local_count(P) * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  else
+    RET(download_vector(P, P->x, x_host));
   CU(cudaStreamSynchronize(P->stream));
   return B200CG_OK;
 }
@@ -900,6 +944,8 @@ extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host
   CU(cudaSetDevice(P->desc.device));
   cudaStream_t s = P->stream;
   const long long cnt = local_count(P);
+  if ((op == B200CG_OP_CSR) != P->solution_in_csr)
+    return fail(B200CG_ERR_STATE, "postprocess operator differs from the operator of the last solve");
   if (residual_host) {
     if (op == B200CG_OP_CSR) {
       if (!P->csr.row_map) return fail(B200CG_ERR_STATE, "no CSR matrix in the plan");
@@ -920,9 +966,15 @@ extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host
   }
   if (error_host) {
     if (!P->have_u) return fail(B200CG_ERR_STATE, "error = x - u needs the true solution passed to the last solve");
-    gather_diff_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->x, P->u, P->compact, P->g);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(error_host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (op == B200CG_OP_CSR) {
+      csr_error_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(error_host, P->csr.Az, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      gather_diff_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->x, P->u, P->compact, P->g);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(error_host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
   }
   CU(cudaStreamSynchronize(s));
   return B200CG_OK;

@@ -280,4 +280,11 @@ __global__ void __launch_bounds__(CTA_THREADS) csr_residual_kernel(const CsrArgs
   }
 }
 
+// error = x - u on compact vectors (dirichlet_solver.cpp:172-174); result in Az
+__global__ void __launch_bounds__(CTA_THREADS) csr_error_kernel(const CsrArgs a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows;
+       i += (long long)gridDim.x * blockDim.x)
+    a.Az[i] = __dsub_rn(a.x[i], a.u[i]);
+}
+
 }  // namespace b200cg

@@ -1,0 +1,3 @@
+// Forwarding header: keeps the reference's include name (solver/matrix_free_system.hpp); the classes live in b200_dropin.hpp.
+#pragma once
+#include "b200_dropin.hpp"
