@@ -179,6 +179,9 @@ int cmd_stop(char** a) {
   const int n = std::atoi(a[0]);
   DirichletSolver solver(n, n, 0, 1, 0, 1);
   solver.setSolverParameters(1e-300, 1e-300, 1e-300, 2000000000);
+  solver.enablePrecisionStopping(false);  // only the iteration cap remains: the solve runs until it is stopped
+  solver.enableResidualStopping(false);
+  solver.enableErrorStopping(false);
   std::thread stopper([&] {
     std::this_thread::sleep_for(std::chrono::milliseconds(300));
     solver.requestStop();
