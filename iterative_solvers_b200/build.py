@@ -11,6 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200cg.so")
 DROPIN_DIR = os.path.join(PKG, "dropin")
+DROPIN_LIB = os.path.join(PKG, "libb200_dropin.so")
 DROPIN_TEST = os.path.join(PKG, "dropin_test")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -40,17 +41,19 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_dropin_test(force: bool = False) -> str | None:
-    """C++ host classes mirroring the reference's public surface + their test driver."""
+    """C++ host classes mirroring the reference's public surface (libb200_dropin.so) + their test driver."""
     if not os.path.isdir(DROPIN_DIR):
         return None
-    srcs = _sources(DROPIN_DIR, (".cpp",))
-    deps = srcs + _sources(DROPIN_DIR, (".hpp", ".h")) + [LIB]
-    if force or _newer(DROPIN_TEST, deps):
-        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", DROPIN_TEST, *srcs,
-               "-I", DROPIN_DIR, "-I", os.path.join(ROOT, "include"), "-L", PKG, "-lb200cg",
-               f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN", "-lpthread"]
-        subprocess.check_call(cmd)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    hdrs = _sources(DROPIN_DIR, (".hpp", ".h")) + [os.path.join(ROOT, "include", "b200cg.h")]
+    common = ["-std=c++17", "-O2", "-Wall", "-Wextra", "-I", DROPIN_DIR, "-I", os.path.join(ROOT, "include"),
+              "-L", PKG, f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN"]
+    lib_src = os.path.join(DROPIN_DIR, "b200_dropin.cpp")
+    if force or _newer(DROPIN_LIB, [lib_src, LIB] + hdrs):
+        subprocess.check_call([cxx, "-fPIC", "-shared", "-o", DROPIN_LIB, lib_src, *common, "-lb200cg"])
+    test_src = os.path.join(DROPIN_DIR, "dropin_test.cpp")
+    if force or _newer(DROPIN_TEST, [test_src, DROPIN_LIB] + hdrs):
+        subprocess.check_call([cxx, "-o", DROPIN_TEST, test_src, *common, "-lb200_dropin", "-lb200cg", "-lpthread"])
     return DROPIN_TEST
 
 
