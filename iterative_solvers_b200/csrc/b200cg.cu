@@ -56,14 +56,19 @@ struct GraphEntry {
   int kernels = 0;
 };
 
+struct TileTable {
+  Tile* d_tiles = nullptr;
+  int* d_cta_begin = nullptr;
+  int grid = 0, n_tiles = 0;
+};
+
 struct b200cg_plan_s {
   b200cg_plan_desc desc;
   Geom g;
   int sms = 148;
-  int ctas_per_sm = 2;  // resident CTAs of the persistent sweep kernel per SM
-  Tile* d_tiles = nullptr;
-  int* d_cta_begin = nullptr;
-  int sweep_grid = 0, n_tiles = 0;
+  TileTable tile_tab[2];  // sweep work lists for 2 and 3 resident CTAs per SM
+  int shape_dot = 0, shape_upd = 0, shape_nox = 0;  // launch shapes of the hot flavours (launch_tile)
+  bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
   double* r[2] = {nullptr, nullptr};
@@ -180,7 +185,8 @@ static int setup_geometry(b200cg_plan_s* P) {
 // equal ranges (split where a range crosses a strip end) and give CTA c the ranges c, c + grid, ... - every
 // CTA gets the same number of rows to within one, and a tile's two halo rows are amortised over its height.
 // desc.tile_rows > 0 forces fixed-height tiles instead (tests: ragged heights, many tiles per CTA).
-static void build_tiles(b200cg_plan_s* P, std::vector<Tile>* tiles, std::vector<int>* cta_begin, int* grid_out) {
+static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* tiles, std::vector<int>* cta_begin,
+                        int* grid_out) {
   const Geom& g = P->g;
   struct Col { int col0, y0, y1, xlo; };
   std::vector<Col> cols;  // one entry per (block, strip)
@@ -193,7 +199,7 @@ static void build_tiles(b200cg_plan_s* P, std::vector<Tile>* tiles, std::vector<
     for (int s = 0; s < strips; ++s) cols.push_back({s * STRIP_OUT, yU0, yU1, 1});
   long long total = 0;
   for (const Col& c : cols) total += c.y1 - c.y0;
-  const int max_grid = P->sms * P->ctas_per_sm;
+  const int max_grid = P->sms * ctas_per_sm;
   std::vector<std::vector<Tile>> per_cta;
   if (P->desc.tile_rows > 0) {
     std::vector<Tile> all;
@@ -295,8 +301,10 @@ static void free_plan(b200cg_plan_s* P) {
   cudaFree(P->d_state);
   cudaFree(P->d_log);
   cudaFree(P->d_partials);
-  cudaFree(P->d_tiles);
-  cudaFree(P->d_cta_begin);
+  for (auto& tt : P->tile_tab) {
+    cudaFree(tt.d_tiles);
+    cudaFree(tt.d_cta_begin);
+  }
   if (P->h_state) cudaFreeHost(P->h_state);
   if (P->h_log) cudaFreeHost(P->h_log);
   for (auto& e : P->ev)
@@ -345,15 +353,26 @@ static int plan_create_impl(b200cg_plan_s* P) {
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
-  if (!P->generic) {
+  for (int t = 0; t < 2 && !P->generic; ++t) {
     std::vector<Tile> tiles;
     std::vector<int> cta_begin;
-    build_tiles(P, &tiles, &cta_begin, &P->sweep_grid);
-    P->n_tiles = (int)tiles.size();
-    CU(cudaMalloc(&P->d_tiles, std::max<size_t>(tiles.size(), 1) * sizeof(Tile)));
-    CU(cudaMalloc(&P->d_cta_begin, cta_begin.size() * sizeof(int)));
-    if (!tiles.empty()) CU(cudaMemcpy(P->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(P->d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TileTable& tt = P->tile_tab[t];
+    build_tiles(P, 2 + t, &tiles, &cta_begin, &tt.grid);
+    tt.n_tiles = (int)tiles.size();
+    CU(cudaMalloc(&tt.d_tiles, std::max<size_t>(tiles.size(), 1) * sizeof(Tile)));
+    CU(cudaMalloc(&tt.d_cta_begin, cta_begin.size() * sizeof(int)));
+    if (!tiles.empty()) CU(cudaMemcpy(tt.d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(tt.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  {
+    auto env_int = [](const char* name, int dflt) {
+      const char* v = getenv(name);
+      return v ? atoi(v) : dflt;
+    };
+    P->shape_dot = env_int("B200CG_SHAPE_DOT", P->shape_dot);
+    P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
+    P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
+    P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
   }
   P->partial_slots = P->sms * 16 + 64;
   CU(cudaMalloc(&P->d_partials, sizeof(double) * MAX_PARTIALS * (size_t)P->partial_slots));
@@ -512,20 +531,33 @@ extern "C" int b200cg_get_coords(b200cg_plan_t P, double* xs, double* ys) {
 }
 
 // ------------------------------------------------------------------------------------------- operator
-// Stage geometry per kernel flavour: HS rows per stage, NST stages; ~96 KB of bulk-copy destinations per CTA
-// so that two CTAs stay resident per SM.
-template <int MODE, int FLAGS>
-struct StreamShape {
-  static constexpr int NSTREAM = StreamCfg<MODE, FLAGS>::NSTREAM;
-  static constexpr int HS = 2;
-  static constexpr int NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 6 : (NSTREAM == 3 ? 4 : 3));
+// Launch shapes of the sweep kernel. A shape = rows per stage (HS), stages (NST), resident CTAs per SM (CTAS);
+// the bulk-copy destinations take ~96 KB per CTA at 2 CTAs/SM and ~64-72 KB at 3. Shape 0 is the default; the
+// others exist for the hot flavours only and are selected per plan with B200CG_SHAPE_DOT / _UPD / _NOX
+// (tuning knobs).
+template <int NSTREAM, int SHAPE>
+struct ShapeOf;
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 0> {  // HS = 2, 2 CTAs/SM
+  static constexpr int HS = 2, CTAS = 2, NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 6 : (NSTREAM == 3 ? 4 : 3));
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 1> {  // HS = 2, 3 CTAs/SM
+  static constexpr int HS = 2, CTAS = 3, NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 4 : 3);
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 2> {  // HS = 4, 2 CTAs/SM
+  static constexpr int HS = 4, CTAS = 2, NST = NSTREAM == 1 ? 6 : (NSTREAM == 2 ? 3 : 2);
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 3> {  // HS = 4, 3 CTAs/SM (two-stream flavours only)
+  static constexpr int HS = 4, CTAS = 3, NST = 2;
 };
 
-template <int MODE, int FLAGS>
-static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (P->n_tiles <= 0) return B200CG_OK;
-  using Sh = StreamShape<MODE, FLAGS>;
-  auto kernel = cg_stream_kernel<MODE, FLAGS, Sh::HS, Sh::NST>;
+template <int MODE, int FLAGS, int SHAPE>
+static int launch_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
+  using Sh = ShapeOf<StreamCfg<MODE, FLAGS>::NSTREAM, SHAPE>;
+  auto kernel = cg_stream_kernel<MODE, FLAGS, Sh::HS, Sh::NST, Sh::CTAS>;
   constexpr size_t smem = stream_smem_bytes<MODE, FLAGS, Sh::HS, Sh::NST>();
   static thread_local bool configured[64] = {};
   const int dev = P->desc.device & 63;
@@ -533,9 +565,33 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = true;
   }
-  kernel<<<P->sweep_grid, STREAM_THREADS, smem, s>>>(a);
+  const TileTable& tt = P->tile_tab[Sh::CTAS - 2];
+  if (tt.n_tiles <= 0) return B200CG_OK;
+  a.tiles = tt.d_tiles;
+  a.cta_begin = tt.d_cta_begin;
+  kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
+}
+
+// hot flavours get every shape; the rest run shape 0
+template <int MODE, int FLAGS>
+static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  constexpr bool hot = (MODE == MODE_DOT && FLAGS == 0) ||
+                       (MODE == MODE_UPD && (FLAGS == 0 || FLAGS == F_NOX || FLAGS == F_X2));
+  if constexpr (hot) {
+    constexpr int nstream = StreamCfg<MODE, FLAGS>::NSTREAM;
+    const int shape = MODE == MODE_DOT ? P->shape_dot : (FLAGS == F_NOX ? P->shape_nox : P->shape_upd);
+    switch (shape) {
+      case 1: return launch_shape<MODE, FLAGS, 1>(P, a, s);
+      case 2: return launch_shape<MODE, FLAGS, 2>(P, a, s);
+      case 3:
+        if constexpr (nstream == 2) return launch_shape<MODE, FLAGS, 3>(P, a, s);
+        break;
+      default: break;
+    }
+  }
+  return launch_shape<MODE, FLAGS, 0>(P, a, s);
 }
 
 static TileArgs base_args(b200cg_plan_s* P) {
@@ -544,8 +600,6 @@ static TileArgs base_args(b200cg_plan_s* P) {
   a.st = P->d_state;
   a.partials = P->d_partials;
   a.cb_log = P->d_log;
-  a.tiles = P->d_tiles;
-  a.cta_begin = P->d_cta_begin;
   a.defer = P->desc.world > 1 ? 1 : 0;
   a.g = P->g;
   return a;
@@ -627,13 +681,13 @@ extern "C" int b200cg_csr_apply(b200cg_plan_t P, const double* x_host, double* y
 }
 
 // ------------------------------------------------------------------------------------------- solve
-enum { V_U = 1, V_REPORT = 2, V_CSR = 4 };
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8 };
 
 // Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
 // read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
 static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
   cudaStream_t s = P->stream;
-  const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR;
+  const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR, xdefer = variant & V_XDEFER;
   int kernels = 0;
   CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200CG_OK;
@@ -663,7 +717,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     a.r_out = P->r[par ^ 1];
     a.p_out = P->p[par ^ 1];
     a.u = P->u;
-    const int fl = (with_u ? F_U : 0) | (report ? F_REPORT : 0);
+    const int fl = xdefer ? ((k & 1) ? F_X2 : F_NOX) : ((with_u ? F_U : 0) | (report ? F_REPORT : 0));
     rc = launch_tile<MODE_DOT, 0>(P, a, s);
     ++kernels;
     if (rc == B200CG_OK && P->desc.world > 1) {
@@ -672,7 +726,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     }
     if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
     if (rc != B200CG_OK) break;
-    if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
+    if (xdefer) rc = (k & 1) ? launch_tile<MODE_UPD, F_X2>(P, a, s) : launch_tile<MODE_UPD, F_NOX>(P, a, s);
+    else if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
     else if (report) rc = launch_tile<MODE_UPD, F_REPORT>(P, a, s);
     else if (with_u) rc = launch_tile<MODE_UPD, F_U>(P, a, s);
     else rc = launch_tile<MODE_UPD, 0>(P, a, s);
@@ -834,7 +889,9 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
   K = std::max(2, (K + 1) & ~1);
   K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
-  const int variant = (with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0);
+  // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
+  const bool xdefer = P->x_deferral && !csr && !report && prm->rule == B200CG_RULE_REL_L2;
+  const int variant = xdefer ? V_XDEFER : ((with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0));
   const int key = variant * 4096 + K;
   GraphEntry& ge = P->graphs[key];
   if (!ge.exec) RET(build_graph(P, variant, K, &ge));
@@ -886,6 +943,13 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
 
   // ---- outputs
   const DevState st = *P->h_state;
+  if (xdefer && st.x_pending) {  // the loop ended on an even iteration: settle x += alpha * p
+    const Geom& g = P->g;
+    const size_t begin = (size_t)(g.ylo - g.ybase) * g.pitch, count = (size_t)(g.yhi - g.ylo) * g.pitch;
+    x_flush_kernel<<<ew_grid(P, (long long)(count / 2)), CTA_THREADS, 0, s>>>(P->x, P->p[st.it & 1], P->d_state, begin, count);
+    CU(cudaGetLastError());
+    info->kernel_launches += 1;
+  }
   P->solution_in_csr = csr;
   if (!prm->keep_x_on_device) {
     if (csr) {

@@ -48,6 +48,7 @@ struct DevState {
   double rz;         // r.p   (MSG flavour numerator, msg_solver.cpp:96)
   double pAp;        // p.Ap
   double alpha, beta;
+  double alpha_prev; // x-deferral: alpha of the iteration whose x update is pending
   double r0_norm, r_norm;
   double r_max, dx_max, err_max;
   double dx_l2, err_l2, res_l2;  // MatrixFreeSolver callback quantities (matrix_free_system.cpp:444-463)
@@ -66,7 +67,7 @@ struct DevState {
   unsigned int ticket;
   unsigned int n_log; // callback records appended so far
   int report_pending; // MatrixFreeSolver callback: the update phase asks the report kernel to run
-  int pad;
+  int x_pending;      // x-deferral: the last iteration did not touch x; x += alpha_prev * p is owed
 };
 
 struct CbRecord {

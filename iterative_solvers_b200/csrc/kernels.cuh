@@ -26,6 +26,8 @@ __device__ __forceinline__ void finalize_init(DevState* st, CbRecord* log, doubl
   st->converged = 0;
   st->stop_reason = 0;
   st->report_pending = 0;
+  st->x_pending = 0;
+  st->alpha_prev = 0.0;
   int done = 0;
   if (st->rule == 0) {
     if (!(0 < st->max_it && r0 > st->eps_rel * r0)) {
@@ -97,9 +99,26 @@ __global__ void finalize_kernel(DevState* st, CbRecord* log, int which, int flag
     if (st->done) return;
     finalize_update(st, log, st->loc_s[0], st->loc_m[0], st->loc_m[1], has_u ? st->loc_m[2] : DBL_MAX,
                     report ? st->loc_s[1] : 0.0, (report && has_u) ? st->loc_s[2] : 0.0, report);
+    note_x_deferral(st, flags);
   } else {
     if (!st->report_pending) return;
     finalize_report(st, log, st->loc_s[0], has_u ? st->loc_s[1] : 0.0, has_u);
+  }
+}
+
+// x += alpha_prev * p over the owned rows: settles the update an even (NOX) last iteration left pending.
+__global__ void __launch_bounds__(CTA_THREADS) x_flush_kernel(double* __restrict__ x, const double* __restrict__ p,
+                                                             DevState* st, size_t begin, size_t count) {
+  if (!st->x_pending) return;
+  const double alpha = st->alpha_prev;
+  const size_t n2 = count / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = begin + 2 * i;
+    const double2 pv = __ldg(reinterpret_cast<const double2*>(p + o));
+    double2 xv = *reinterpret_cast<const double2*>(x + o);
+    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+    st2(x + o, xv);
   }
 }
 

@@ -18,7 +18,9 @@ enum { MODE_DOT = 0, MODE_UPD = 1, MODE_APPLY = 2 };
 enum {
   F_U = 1,       // UPD / APPLY-report: also read the true solution u
   F_REPORT = 2,  // UPD: reduce |dx|_2, |x-u|_2.  APPLY: reduce |b - A v|_2, append the callback record, no store
-  F_SUB_B = 4    // APPLY: out = A v - b
+  F_SUB_B = 4,   // APPLY: out = A v - b
+  F_NOX = 8,     // UPD, x-deferral: even iteration, x is not touched (its update stays pending)
+  F_X2 = 16      // UPD, x-deferral: odd iteration, applies the pending update and this one
 };
 
 struct TileArgs {
@@ -151,6 +153,16 @@ __device__ __forceinline__ void finalize_report(DevState* st, CbRecord* log, dou
   if (has_u) st->err_l2 = sqrt(err2);
   append_record(st, log, (double)(st->it - 1), st->dx_l2, st->res_l2, st->err_l2);
   st->report_pending = 0;
+}
+
+// x-deferral bookkeeping after an update phase: a NOX iteration leaves x += alpha*p pending.
+__device__ __forceinline__ void note_x_deferral(DevState* st, int flags) {
+  if (flags & F_NOX) {
+    st->alpha_prev = st->alpha;
+    st->x_pending = 1;
+  } else {
+    st->x_pending = 0;
+  }
 }
 
 // Stop rules, evaluated by one thread after the update phase.

@@ -69,7 +69,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int MODE, int FLAGS>
 struct StreamCfg {
   static constexpr bool LOAD_R = (MODE != MODE_APPLY) || (FLAGS & (F_SUB_B | F_REPORT));
-  static constexpr bool LOAD_X = (MODE == MODE_UPD);
+  static constexpr bool LOAD_X = (MODE == MODE_UPD) && !(FLAGS & F_NOX);
   static constexpr bool LOAD_U = (FLAGS & F_U) != 0;
   static constexpr bool REPORT = (FLAGS & F_REPORT) != 0;
   static constexpr int NSTREAM = 1 + (LOAD_R ? 1 : 0) + (LOAD_X ? 1 : 0) + (LOAD_U ? 1 : 0);
@@ -78,12 +78,16 @@ struct StreamCfg {
 };
 
 template <int MODE, int FLAGS, int HS, int NST>
-constexpr size_t stream_smem_bytes() {
+constexpr size_t stream_smem_bytes() {  // (independent of CTAS)
   return (size_t)NST * HS * StreamCfg<MODE, FLAGS>::NSTREAM * ROW_BYTES + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
 }
 
-template <int MODE, int FLAGS, int HS, int NST>
-__global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const TileArgs a) {
+template <int MODE, int FLAGS, int HS, int NST, int CTAS>
+__global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const TileArgs a) {
+  // x-deferral (REL_L2 rule without report): x is only touched every other iteration. F_NOX = even iteration,
+  // x untouched, the state remembers alpha; F_X2 = odd iteration, x += alpha_prev*p_old + alpha*p in the
+  // reference's order of additions, so x is bit-identical to updating it every iteration.
+  constexpr bool NOX = (FLAGS & F_NOX) != 0, X2 = (FLAGS & F_X2) != 0;
   using Cfg = StreamCfg<MODE, FLAGS>;
   constexpr bool LOAD_R = Cfg::LOAD_R, LOAD_X = Cfg::LOAD_X, LOAD_U = Cfg::LOAD_U, REPORT = Cfg::REPORT;
   constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, NM = Cfg::NM;
@@ -170,10 +174,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
   } else {
     // ================================================================ consumers
     const double cA = g.A, cxk = g.xk, cyk = g.yk;
-    double alpha = 0.0, beta = 0.0;
+    double alpha = 0.0, beta = 0.0, alpha_prev = 0.0;
     if (MODE != MODE_APPLY) {
       beta = st->beta;
       if (MODE == MODE_UPD) alpha = st->alpha;
+      if (X2) alpha_prev = st->alpha_prev;
     }
     const size_t pitch = (size_t)g.pitch;
     const bool is_out = (tid >= STRIP_HALO / 2) && (tid < CONS_THREADS - STRIP_HALO / 2);
@@ -187,6 +192,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
     size_t eoff = 0;
     double2 pm = make_double2(0.0, 0.0), pc = make_double2(0.0, 0.0);
     double2 r_prev = make_double2(0.0, 0.0), x_prev = make_double2(0.0, 0.0), u_prev = make_double2(0.0, 0.0);
+    double2 q_prev = make_double2(0.0, 0.0);  // p_old of the row being emitted (X2 only)
     double Lp = 0.0, Rp = 0.0;
 
     for (;;) {
@@ -267,14 +273,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
             acc_s[1] = fma(r1, p1, acc_s[1]);
           } else if (MODE == MODE_UPD) {
             // x += alpha p; r -= alpha Ap (matrix_free_system.cpp:422-429)
-            const double xo0 = v0 ? x_prev.x : 0.0, xo1 = v1 ? x_prev.y : 0.0;
+            double xo0 = v0 ? x_prev.x : 0.0, xo1 = v1 ? x_prev.y : 0.0;
+            if (X2) {  // the update the previous (NOX) iteration left pending: x += alpha_prev * p_old
+              xo0 = __dadd_rn(xo0, __dmul_rn(alpha_prev, v0 ? q_prev.x : 0.0));
+              xo1 = __dadd_rn(xo1, __dmul_rn(alpha_prev, v1 ? q_prev.y : 0.0));
+            }
             double2 xn, rn;
             xn.x = __dadd_rn(xo0, __dmul_rn(alpha, p0));
             xn.y = __dadd_rn(xo1, __dmul_rn(alpha, p1));
             rn.x = __dsub_rn(r0, __dmul_rn(alpha, ap0));
             rn.y = __dsub_rn(r1, __dmul_rn(alpha, ap1));
             if (st_ok) {
-              st2(a.x + eoff, xn);
+              if (!NOX) st2(a.x + eoff, xn);
               st2(a.r_out + eoff, rn);
               st2(a.p_out + eoff, make_double2(p0, p1));
             }
@@ -330,6 +340,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
         r_prev = cur_r;
         x_prev = cur_x;
         u_prev = cur_u;
+        if (X2) q_prev = cur_p;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -353,6 +364,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2) cg_stream_kernel(const Tile
   } else if (MODE == MODE_UPD) {
     finalize_update(st, a.cb_log, acc_s[0], acc_m[0], acc_m[1], LOAD_U ? acc_m[NM - 1] : DBL_MAX,
                     REPORT ? acc_s[1] : 0.0, (REPORT && LOAD_U) ? acc_s[2] : 0.0, REPORT);
+    note_x_deferral(st, FLAGS);
   } else if (REPORT) {
     finalize_report(st, a.cb_log, acc_s[0], LOAD_U ? acc_s[1] : 0.0, LOAD_U);
   }
