@@ -118,7 +118,10 @@ typedef struct {
   double upd_kernel_ms;    /* (CUDA event nodes around the first iteration of every graph launch) */
   int kernel_samples;
   int64_t local_unknowns;  /* unknowns owned by this rank */
-  int reserved[6];
+  double upd_even_ms;      /* sampled update-phase kernel of even / odd iterations: with x-deferral (REL_L2 rule, */
+  double upd_odd_ms;       /* no report) even iterations skip x (32 B/unknown) and odd ones carry both (48 B)    */
+  int x_deferral;          /* 1 if this solve touched x only every other iteration */
+  int reserved[5];
 } b200cg_info;
 
 /* (iteration, precision, residual, error) - Solver::setIterationCallback, solver.hpp:46-50. Called on the

@@ -53,7 +53,8 @@ class SolveInfo(C.Structure):
                 ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("dot_kernel_ms", C.c_double),
                 ("upd_kernel_ms", C.c_double), ("kernel_samples", C.c_int), ("local_unknowns", C.c_int64),
-                ("reserved", C.c_int * 6)]
+                ("upd_even_ms", C.c_double), ("upd_odd_ms", C.c_double), ("x_deferral", C.c_int),
+                ("reserved", C.c_int * 5)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -67,7 +67,7 @@ struct b200cg_plan_s {
   Geom g;
   int sms = 148;
   TileTable tile_tab[2];  // sweep work lists for 2 and 3 resident CTAs per SM
-  int shape_dot = 0, shape_upd = 0, shape_nox = 0;  // launch shapes of the hot flavours (launch_tile)
+  int shape_dot = 3, shape_upd = 2, shape_nox = 3;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
@@ -85,7 +85,7 @@ struct b200cg_plan_s {
   CbRecord* h_log = nullptr;  // pinned mirror
   double* d_partials = nullptr;
   int partial_slots = 0;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
   bool have_rhs = false, have_u = false, have_solution = false;
   bool generic = false;          // B200CG_DOMAIN_GENERIC: CSR entry points only, no pitched vectors
   bool solution_in_csr = false;  // the last solve ran on the assembled path
@@ -725,6 +725,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       ++kernels;
     }
     if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+    if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
     if (rc != B200CG_OK) break;
     if (xdefer) rc = (k & 1) ? launch_tile<MODE_UPD, F_X2>(P, a, s) : launch_tile<MODE_UPD, F_NOX>(P, a, s);
     else if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
@@ -739,6 +740,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       if (rc == B200CG_OK) rc = exchange_halo(P, P->p[par ^ 1]);
     }
     if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+    if (k == 1 && !report) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
     if (rc == B200CG_OK && report) {
       TileArgs ra = base_args(P);
       ra.p_in = P->x;
@@ -899,31 +901,38 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   CU(cudaEventRecord(P->ev[5], s));
   unsigned int consumed = 0;
   bool interrupted = false;
-  double dot_ms = 0.0, upd_ms = 0.0;
-  int samples = 0;
+  double dot_ms = 0.0, upd_even = 0.0, upd_odd = 0.0;
+  int samples = 0, it_before = 0;
   // the init kernel's verdict (0 iterations) and record come back with the first graph launch
   for (;;) {
     CU(cudaGraphLaunch(ge.exec, s));
     info->kernel_launches += ge.kernels;
     CU(cudaStreamSynchronize(s));
     const DevState& st = *P->h_state;
-    if (consumed == 0 && st.it > 0) {  // kernels of the first captured iteration really ran in this launch
-      float a = 0.f, b = 0.f;
-      if (cudaEventElapsedTime(&a, P->ev[0], P->ev[1]) == cudaSuccess &&
-          cudaEventElapsedTime(&b, P->ev[1], P->ev[2]) == cudaSuccess) {
-        dot_ms += a;
-        upd_ms += b;
+    // Event nodes bracket the kernels of the first two captured iterations; count the sample only if those
+    // iterations really ran in this launch (it advanced by at least 2 and the run was not already over).
+    if (!csr && !report && st.it - it_before >= 2) {
+      float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
+      if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
+          cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess &&
+          cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
+        dot_ms += 0.5 * (d0 + d1);
+        upd_even += u0;
+        upd_odd += u1;
         ++samples;
       }
-    } else if (st.it > 0 && !st.done) {
-      float a = 0.f, b = 0.f;
-      if (cudaEventElapsedTime(&a, P->ev[0], P->ev[1]) == cudaSuccess &&
-          cudaEventElapsedTime(&b, P->ev[1], P->ev[2]) == cudaSuccess) {
-        dot_ms += a;
-        upd_ms += b;
+    } else if ((csr || report) && st.it - it_before >= 1) {
+      float d0 = 0.f, u0 = 0.f;
+      if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
+        dot_ms += d0;
+        upd_even += u0;
+        upd_odd += u0;
         ++samples;
       }
     }
+    it_before = st.it;
     if (cb) {
       for (; consumed < st.n_log; ++consumed) {
         const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
@@ -982,7 +991,10 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   cudaEventElapsedTime(&ms, P->ev[3], P->ev[7]);
   info->device_ms = ms;
   info->dot_kernel_ms = samples ? dot_ms / samples : 0.0;
-  info->upd_kernel_ms = samples ? upd_ms / samples : 0.0;
+  info->upd_kernel_ms = samples ? 0.5 * (upd_even + upd_odd) / samples : 0.0;
+  info->upd_even_ms = samples ? upd_even / samples : 0.0;
+  info->upd_odd_ms = samples ? upd_odd / samples : 0.0;
+  info->x_deferral = xdefer ? 1 : 0;
   info->kernel_samples = samples;
   // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
   if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);

@@ -10,6 +10,9 @@
 // reference's only through the summation order of the dot products.
 #pragma once
 #include <float.h>
+#ifndef B200CG_STORE_HINT
+#define B200CG_STORE_HINT 1
+#endif
 #include "common.cuh"
 
 namespace b200cg {
@@ -49,6 +52,16 @@ __device__ __forceinline__ double2 ld_rw2(const double* p, bool ok) {
   return ok ? *reinterpret_cast<const double2*>(p) : make_double2(0.0, 0.0);
 }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+// sweep outputs: written once, next read a whole sweep (GBs) later
+__device__ __forceinline__ void st2_out(double* p, double2 v) {
+#if B200CG_STORE_HINT == 1
+  __stcs(reinterpret_cast<double2*>(p), v);  // st.global.cs: evict-first
+#elif B200CG_STORE_HINT == 2
+  __stwt(reinterpret_cast<double2*>(p), v);  // st.global.wt: write-through
+#else
+  *reinterpret_cast<double2*>(p) = v;
+#endif
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -284,9 +284,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
             rn.x = __dsub_rn(r0, __dmul_rn(alpha, ap0));
             rn.y = __dsub_rn(r1, __dmul_rn(alpha, ap1));
             if (st_ok) {
-              if (!NOX) st2(a.x + eoff, xn);
-              st2(a.r_out + eoff, rn);
-              st2(a.p_out + eoff, make_double2(p0, p1));
+              if (!NOX) st2_out(a.x + eoff, xn);
+              st2_out(a.r_out + eoff, rn);
+              st2_out(a.p_out + eoff, make_double2(p0, p1));
             }
             acc_s[0] = fma(rn.x, rn.x, acc_s[0]);
             acc_s[0] = fma(rn.y, rn.y, acc_s[0]);
