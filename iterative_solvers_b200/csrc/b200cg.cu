@@ -480,6 +480,13 @@ static int exchange_halo(b200cg_plan_s* P, double* v) {
       return fail(B200CG_ERR_UNSUPPORTED, "%s needs a geometric plan (this one is B200CG_DOMAIN_GENERIC)", __func__); \
   } while (0)
 
+static int exchange_halo2(b200cg_plan_s* P, double* v0, double* v1) {
+  if (P->desc.world <= 1) return B200CG_OK;
+  std::string err;
+  if (!comm_halo2(&P->comm, v0, v1, P->g.yrows, P->g.pitch, P->stream, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  return B200CG_OK;
+}
+
 extern "C" int b200cg_build_rhs(b200cg_plan_t P) {
   if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
   NEED_GEOMETRY(P);
@@ -734,10 +741,9 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     else rc = launch_tile<MODE_UPD, 0>(P, a, s);
     ++kernels;
     if (rc == B200CG_OK && P->desc.world > 1) {
-      rc = reduce_and_finalize(P, 2, fl, true, s);
+      rc = reduce_and_finalize(P, 2, fl, /*with_max=*/!xdefer, s);
       ++kernels;
-      if (rc == B200CG_OK) rc = exchange_halo(P, P->r[par ^ 1]);
-      if (rc == B200CG_OK) rc = exchange_halo(P, P->p[par ^ 1]);
+      if (rc == B200CG_OK) rc = exchange_halo2(P, P->r[par ^ 1], P->p[par ^ 1]);
     }
     if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
     if (k == 1 && !report) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
@@ -880,8 +886,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
     info->kernel_launches += 1;
     if (P->desc.world > 1) {
       RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
-      RET(exchange_halo(P, P->r[0]));
-      RET(exchange_halo(P, P->p[0]));
+      RET(exchange_halo2(P, P->r[0], P->p[0]));
       info->kernel_launches += 1;
     }
   }

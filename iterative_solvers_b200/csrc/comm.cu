@@ -107,6 +107,29 @@ bool comm_halo(Comm* c, const double* first_owned, const double* last_owned, dou
   return ok && check(r, "ncclGroupEnd", err);
 }
 
+bool comm_halo2(Comm* c, double* v0, double* v1, int yrows, int pitch, cudaStream_t s, std::string* err) {
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  if (!check(g_api.GroupStart(), "ncclGroupStart", err)) return false;
+  bool ok = true;
+  double* vs[2] = {v0, v1};
+  for (double* v : vs) {
+    double* first_owned = v + (size_t)1 * pitch;
+    double* last_owned = v + (size_t)(yrows - 2) * pitch;
+    double* halo_below = v;
+    double* halo_above = v + (size_t)(yrows - 1) * pitch;
+    if (c->rank > 0) {
+      ok = ok && check(g_api.Send(first_owned, pitch, ncclDouble, c->rank - 1, comm, s), "ncclSend", err);
+      ok = ok && check(g_api.Recv(halo_below, pitch, ncclDouble, c->rank - 1, comm, s), "ncclRecv", err);
+    }
+    if (c->rank < c->world - 1) {
+      ok = ok && check(g_api.Send(last_owned, pitch, ncclDouble, c->rank + 1, comm, s), "ncclSend", err);
+      ok = ok && check(g_api.Recv(halo_above, pitch, ncclDouble, c->rank + 1, comm, s), "ncclRecv", err);
+    }
+  }
+  ncclResult_t r = g_api.GroupEnd();
+  return ok && check(r, "ncclGroupEnd", err);
+}
+
 bool comm_allreduce_state(Comm* c, DevState* st, bool with_max, cudaStream_t s, std::string* err) {
   ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
   double* sums = reinterpret_cast<double*>(reinterpret_cast<char*>(st) + offsetof(DevState, loc_s));

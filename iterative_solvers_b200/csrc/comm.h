@@ -21,6 +21,8 @@ void comm_destroy(Comm* c);
 // exchange one row (count doubles) with both neighbours: send first/last owned rows, receive into the halo rows
 bool comm_halo(Comm* c, const double* first_owned, const double* last_owned, double* halo_below, double* halo_above,
                int count, cudaStream_t s, std::string* err);
+// the same for two vectors (r and p) in one NCCL group = one launch
+bool comm_halo2(Comm* c, double* v0, double* v1, int yrows, int pitch, cudaStream_t s, std::string* err);
 // in-place all-reduce of st->loc_s (sum, 4 doubles) and optionally st->loc_m (max, 4 doubles)
 bool comm_allreduce_state(Comm* c, DevState* st, bool with_max, cudaStream_t s, std::string* err);
 
