@@ -97,7 +97,10 @@ typedef struct {
                               b_host is ignored and no H2D copy happens */
   int keep_x_on_device;    /* 1: skip the D2H copy of the solution (x_host may be NULL) */
   int iters_per_graph;     /* CG iterations captured per CUDA-graph launch; 0 = default */
-  int reserved[7];
+  int small_grid_path;     /* grids that fit the shared memory of one thread-block cluster (about 300^2) are solved by
+                              a single cluster-resident kernel instead of the graph loop: 0 = automatic, 1 = never,
+                              2 = require it (B200CG_ERR_UNSUPPORTED if the grid does not fit) */
+  int reserved[6];
 } b200cg_params;
 
 typedef struct {
@@ -121,7 +124,8 @@ typedef struct {
   double upd_even_ms;      /* sampled update-phase kernel of even / odd iterations: with x-deferral (REL_L2 rule, */
   double upd_odd_ms;       /* no report) even iterations skip x (32 B/unknown) and odd ones carry both (48 B)    */
   int x_deferral;          /* 1 if this solve touched x only every other iteration */
-  int reserved[5];
+  int cluster_path;        /* 1 if this solve ran as one cluster-resident kernel (small_grid_path) */
+  int reserved[4];
 } b200cg_info;
 
 /* (iteration, precision, residual, error) - Solver::setIterationCallback, solver.hpp:46-50. Called on the

@@ -8,11 +8,13 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200cg.h"
 #include "kernels.cuh"
 #include "csr_kernels.cuh"
+#include "cluster_kernel.cuh"
 #include "comm.h"
 
 using namespace b200cg;
@@ -69,6 +71,8 @@ struct b200cg_plan_s {
   TileTable tile_tab[2];  // sweep work lists for 2 and 3 resident CTAs per SM
   int shape_dot = 3, shape_upd = 2, shape_nox = 3;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
+  bool cluster_enabled = true;                      // small-grid path allowed (B200CG_CLUSTER=0 disables)
+  bool cluster16_ok = false;                        // a 16-CTA cluster of the small-grid kernel can be scheduled
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
   double* r[2] = {nullptr, nullptr};
@@ -83,6 +87,8 @@ struct b200cg_plan_s {
   DevState* h_state = nullptr;  // pinned mirror
   CbRecord* d_log = nullptr;
   CbRecord* h_log = nullptr;  // pinned mirror
+  int* h_stop = nullptr;      // mapped flag the cluster kernel polls (interrupt requests)
+  int* d_stop = nullptr;
   double* d_partials = nullptr;
   int partial_slots = 0;
   cudaEvent_t ev[10] = {};
@@ -307,6 +313,7 @@ static void free_plan(b200cg_plan_s* P) {
   }
   if (P->h_state) cudaFreeHost(P->h_state);
   if (P->h_log) cudaFreeHost(P->h_log);
+  if (P->h_stop) cudaFreeHost(P->h_stop);
   for (auto& e : P->ev)
     if (e) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -353,6 +360,9 @@ static int plan_create_impl(b200cg_plan_s* P) {
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&P->h_stop, sizeof(int), cudaHostAllocMapped));
+  *P->h_stop = 0;
+  CU(cudaHostGetDevicePointer(&P->d_stop, P->h_stop, 0));
   for (int t = 0; t < 2 && !P->generic; ++t) {
     std::vector<Tile> tiles;
     std::vector<int> cta_begin;
@@ -373,6 +383,27 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
+    P->cluster_enabled = env_int("B200CG_CLUSTER", 1) != 0;
+    if (!P->generic && P->cluster_enabled) {
+      // probe once whether the non-portable 16-CTA cluster is schedulable with a full shared-memory carve-out
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16, 1, 1);
+      cfg.blockDim = dim3(CL_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = 200 * 1024;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 16;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+          cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaOccupancyMaxActiveClusters(&nclusters, cg_cluster_kernel, &cfg) == cudaSuccess)
+        P->cluster16_ok = nclusters > 0;
+      cudaGetLastError();
+    }
   }
   P->partial_slots = P->sms * 16 + 64;
   CU(cudaMalloc(&P->d_partials, sizeof(double) * MAX_PARTIALS * (size_t)P->partial_slots));
@@ -782,6 +813,55 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
   return B200CG_OK;
 }
 
+// Small-grid path: how many CTAs a cluster needs to hold r, p, x of the grid in shared memory (0 = does not fit).
+static int cluster_ctas_for(const b200cg_plan_s* P, int* rows_per_cta, size_t* smem) {
+  if (P->generic || P->desc.world > 1) return 0;
+  const Geom& g = P->g;
+  // 8 CTAs (portable cluster size) for the smallest grids, where the per-iteration cost is the three cluster
+  // barriers; 16 CTAs (non-portable size, B200 allows it) once a band would exceed 16 rows: the sweep over the band
+  // is what takes the time there (n = 250: 11.6 us/iteration with 8 CTAs).
+  const int order[2] = {(g.m - 1 > 128 && P->cluster16_ok) ? 16 : 8, (g.m - 1 > 128 && P->cluster16_ok) ? 8 : 16};
+  for (int c : order) {
+    if (c == 16 && !P->cluster16_ok) continue;
+    const int rpc = (g.m - 1 + c - 1) / c;
+    const size_t bytes = cluster_smem_bytes(rpc, g.pitch);
+    if (bytes <= 200 * 1024) {
+      *rows_per_cta = rpc;
+      *smem = bytes;
+      return c;
+    }
+  }
+  return 0;
+}
+
+static int launch_cluster_solve(b200cg_plan_s* P, int ctas, int rows_per_cta, size_t smem, bool with_u, cudaStream_t s) {
+  CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ctas > 8) CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  ClusterArgs ca;
+  ca.b = P->b;
+  ca.u = with_u ? P->u : nullptr;
+  ca.x = P->x;
+  ca.st = P->d_state;
+  ca.cb_log = P->d_log;
+  ca.stop_flag = P->d_stop;
+  ca.g = P->g;
+  ca.rows_per_cta = rows_per_cta;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas, 1, 1);
+  cfg.blockDim = dim3(CL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, cg_cluster_kernel, ca));
+  return B200CG_OK;
+}
+
 static int default_iters_per_graph(const b200cg_plan_s* P) {
   // small grids are launch-bound: long graphs; big grids: keep the stop/interrupt latency around 0.1 s
   const long long n = local_count(P);
@@ -863,96 +943,136 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   *P->h_state = hs;
   CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
 
-  if (csr) {
-    csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
-    CU(cudaGetLastError());
-    info->kernel_launches += 1;
-  } else {
-    const Geom& g = P->g;
-    InitArgs ia;
-    ia.b = P->b;
-    ia.u = with_u ? P->u : nullptr;
-    ia.r = P->r[0];
-    ia.p = P->p[0];
-    ia.x = P->x;
-    ia.st = P->d_state;
-    ia.partials = P->d_partials;
-    ia.cb_log = P->d_log;
-    ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
-    ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
-    ia.defer = P->desc.world > 1 ? 1 : 0;
-    cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
-    CU(cudaGetLastError());
-    info->kernel_launches += 1;
-    if (P->desc.world > 1) {
-      RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
-      RET(exchange_halo2(P, P->r[0], P->p[0]));
-      info->kernel_launches += 1;
-    }
+  // ---- path: grids that fit one thread-block cluster's shared memory run as a single resident kernel
+  int cl_rows = 0;
+  size_t cl_smem = 0;
+  int cl_ctas = 0;
+  {
+    const long long cb_records = 2 + (long long)std::max(prm->max_it, 0) / 100;
+    const bool eligible = !csr && !report && prm->small_grid_path != 1 && P->cluster_enabled &&
+                          !(cb && cb_records > CB_LOG_CAP);
+    if (eligible) cl_ctas = cluster_ctas_for(P, &cl_rows, &cl_smem);
+    if (prm->small_grid_path == 2 && cl_ctas == 0)
+      return fail(B200CG_ERR_UNSUPPORTED, "small_grid_path = 2 but this solve cannot run in one cluster "
+                                          "(grid too large, sharded plan, CSR operator or per-iteration report)");
   }
+  const bool use_cluster = cl_ctas > 0;
 
-  // ---- the captured loop
-  int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
-  if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
-  K = std::max(2, (K + 1) & ~1);
-  K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
-  // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
-  const bool xdefer = P->x_deferral && !csr && !report && prm->rule == B200CG_RULE_REL_L2;
-  const int variant = xdefer ? V_XDEFER : ((with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0));
-  const int key = variant * 4096 + K;
-  GraphEntry& ge = P->graphs[key];
-  if (!ge.exec) RET(build_graph(P, variant, K, &ge));
-
-  CU(cudaEventRecord(P->ev[5], s));
+  bool xdefer = false;
   unsigned int consumed = 0;
   bool interrupted = false;
   double dot_ms = 0.0, upd_even = 0.0, upd_odd = 0.0;
   int samples = 0, it_before = 0;
-  // the init kernel's verdict (0 iterations) and record come back with the first graph launch
-  for (;;) {
-    CU(cudaGraphLaunch(ge.exec, s));
-    info->kernel_launches += ge.kernels;
+  (void)it_before;
+  if (use_cluster) {
+    *P->h_stop = 0;
+    CU(cudaEventRecord(P->ev[5], s));
+    RET(launch_cluster_solve(P, cl_ctas, cl_rows, cl_smem, with_u, s));
+    info->kernel_launches += 1;
+    CU(cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(P->ev[8], s));
+    // the kernel polls the mapped flag every CL_POLL_EVERY iterations; forward the caller's stop request
+    for (int spins = 0; cudaEventQuery(P->ev[8]) == cudaErrorNotReady; ++spins) {
+      if (stop_flag && *stop_flag) *P->h_stop = 1;
+      if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));  // long solve: stop burning a core
+    }
     CU(cudaStreamSynchronize(s));
     const DevState& st = *P->h_state;
-    // Event nodes bracket the kernels of the first two captured iterations; count the sample only if those
-    // iterations really ran in this launch (it advanced by at least 2 and the run was not already over).
-    if (!csr && !report && st.it - it_before >= 2) {
-      float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
-      if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
-          cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
-          cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess &&
-          cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
-        dot_ms += 0.5 * (d0 + d1);
-        upd_even += u0;
-        upd_odd += u1;
-        ++samples;
-      }
-    } else if ((csr || report) && st.it - it_before >= 1) {
-      float d0 = 0.f, u0 = 0.f;
-      if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
-          cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
-        dot_ms += d0;
-        upd_even += u0;
-        upd_odd += u0;
-        ++samples;
-      }
-    }
-    it_before = st.it;
-    if (cb) {
+    interrupted = st.stop_reason == B200CG_STOP_INTERRUPTED;
+    if (cb)
       for (; consumed < st.n_log; ++consumed) {
         const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
         cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
       }
+  } else {
+    if (csr) {
+      csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      info->kernel_launches += 1;
     } else {
-      consumed = st.n_log ? st.n_log : 1;
+      const Geom& g = P->g;
+      InitArgs ia;
+      ia.b = P->b;
+      ia.u = with_u ? P->u : nullptr;
+      ia.r = P->r[0];
+      ia.p = P->p[0];
+      ia.x = P->x;
+      ia.st = P->d_state;
+      ia.partials = P->d_partials;
+      ia.cb_log = P->d_log;
+      ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
+      ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
+      ia.defer = P->desc.world > 1 ? 1 : 0;
+      cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
+      CU(cudaGetLastError());
+      info->kernel_launches += 1;
+      if (P->desc.world > 1) {
+        RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
+        RET(exchange_halo2(P, P->r[0], P->p[0]));
+        info->kernel_launches += 1;
+      }
     }
-    if (consumed == 0) consumed = 1;
-    if (st.done) break;
-    if (stop_flag && *stop_flag) {
-      interrupted = true;
-      break;
+
+    // ---- the captured loop
+    int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
+    if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
+    K = std::max(2, (K + 1) & ~1);
+    K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
+    // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
+    xdefer = P->x_deferral && !csr && !report && prm->rule == B200CG_RULE_REL_L2;
+    const int variant = xdefer ? V_XDEFER : ((with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0));
+    const int key = variant * 4096 + K;
+    GraphEntry& ge = P->graphs[key];
+    if (!ge.exec) RET(build_graph(P, variant, K, &ge));
+
+    CU(cudaEventRecord(P->ev[5], s));
+    // the init kernel's verdict (0 iterations) and record come back with the first graph launch
+    for (;;) {
+      CU(cudaGraphLaunch(ge.exec, s));
+      info->kernel_launches += ge.kernels;
+      CU(cudaStreamSynchronize(s));
+      const DevState& st = *P->h_state;
+      // Event nodes bracket the kernels of the first two captured iterations; count the sample only if those
+      // iterations really ran in this launch (it advanced by at least 2 and the run was not already over).
+      if (!csr && !report && st.it - it_before >= 2) {
+        float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
+        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess &&
+            cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
+          dot_ms += 0.5 * (d0 + d1);
+          upd_even += u0;
+          upd_odd += u1;
+          ++samples;
+        }
+      } else if ((csr || report) && st.it - it_before >= 1) {
+        float d0 = 0.f, u0 = 0.f;
+        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
+          dot_ms += d0;
+          upd_even += u0;
+          upd_odd += u0;
+          ++samples;
+        }
+      }
+      it_before = st.it;
+      if (cb) {
+        for (; consumed < st.n_log; ++consumed) {
+          const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
+          cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
+        }
+      } else {
+        consumed = st.n_log ? st.n_log : 1;
+      }
+      if (consumed == 0) consumed = 1;
+      if (st.done) break;
+      if (stop_flag && *stop_flag) {
+        interrupted = true;
+        break;
+      }
     }
-  }
+}
   CU(cudaEventRecord(P->ev[6], s));
 
   // ---- outputs
@@ -1000,6 +1120,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   info->upd_even_ms = samples ? upd_even / samples : 0.0;
   info->upd_odd_ms = samples ? upd_odd / samples : 0.0;
   info->x_deferral = xdefer ? 1 : 0;
+  info->cluster_path = use_cluster ? 1 : 0;
   info->kernel_samples = samples;
   // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
   if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);

@@ -149,7 +149,7 @@ __device__ __forceinline__ void append_record(DevState* st, CbRecord* log, doubl
   unsigned int k = st->n_log;
   CbRecord rec;
   rec.it = it; rec.precision = p; rec.residual = r; rec.error = e;
-  log[k % CB_LOG_CAP] = rec;
+  if (log) log[k % CB_LOG_CAP] = rec;  // (cluster kernel: only CTA 0 owns the log)
   st->n_log = k + 1;
 }
 

@@ -114,11 +114,15 @@ def test_two_iterations_match_py_debug(capi, golden_scripts, golden_ref):
         assert relmax(x, golden_ref["mf_n6_a1_x2"]) < 1e-14
 
 
+@pytest.mark.parametrize("path", [0, 1], ids=["auto(cluster)", "graph"])
 @pytest.mark.parametrize("n,a_tag,iters", [(6, 1, 13), (30, 1, 88), (64, 0, 178), (128, 0, 352), (128, 1, 362)])
-def test_matrix_free_solve_parity(capi, golden_ref, n, a_tag, iters):
+def test_matrix_free_solve_parity(capi, golden_ref, n, a_tag, iters, path):
+    """Both execution paths: grids this small default to the single cluster-resident kernel (small_grid_path 0);
+    small_grid_path 1 forces the CUDA-graph loop of sweep kernels that large grids use."""
     tag = f"mf_n{n}_a{a_tag}"
     with plan_for(capi, n, a_tag) as p:
-        x, info = p.solve(b=golden_ref[tag + "_rhs"], eps_rel=1e-8, max_it=10000)
+        x, info = p.solve(b=golden_ref[tag + "_rhs"], eps_rel=1e-8, max_it=10000, small_grid_path=path)
+        assert info["cluster_path"] == (1 if path == 0 else 0)
         assert abs(info["iterations"] - iters) <= 1
         assert info["converged"]
         assert relmax(x, golden_ref[tag + "_x"]) < REL
@@ -129,7 +133,7 @@ def test_matrix_free_solve_parity(capi, golden_ref, n, a_tag, iters):
             assert abs(info["r0_l2"] - 5.187466787388469e5) < 1e-6
         # device-built rhs instead of the host one: still inside the bar
         p.build_rhs()
-        x2, info2 = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=10000)
+        x2, info2 = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=10000, small_grid_path=path)
         assert abs(info2["iterations"] - iters) <= 1
         assert relmax(x2, golden_ref[tag + "_x"]) < REL
 
@@ -152,8 +156,29 @@ def test_matrix_free_solver_callback_history(capi, golden_ref):
         assert relmax(x, golden_ref[tag + "_x"]) < REL
 
 
-def test_solve_edge_cases(capi):
+def test_small_grid_path_limits(capi):
+    with plan_for(capi, 1024) as p:  # too large for one cluster's shared memory
+        p.build_rhs()
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=4)
+        assert info["cluster_path"] == 0 and info["iterations"] == 4
+        with pytest.raises(capi.B200CGError) as e:
+            p.solve(rhs_on_device=True, eps_rel=1e-8, max_it=4, small_grid_path=2)
+        assert e.value.status == 6
+    for n, domain in [(250, 0), (301, 1), (4, 0), (2, 1)]:  # largest sizes that still fit, smallest grids
+        with plan_for(capi, n, 0, domain) as p:
+            p.build_rhs()
+            xa, ia = p.solve(rhs_on_device=True, eps_rel=1e-9, max_it=5000, small_grid_path=0)
+            xb, ib = p.solve(rhs_on_device=True, eps_rel=1e-9, max_it=5000, small_grid_path=1)
+            assert ia["cluster_path"] == 1 and ib["cluster_path"] == 0
+            assert abs(ia["iterations"] - ib["iterations"]) <= 1
+            assert relmax(xa, xb) < REL
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["auto(cluster)", "graph"])
+def test_solve_edge_cases(capi, path):
     with plan_for(capi, 30) as p:
+        import functools
+        p.solve = functools.partial(p.solve, small_grid_path=path)
         zero = np.zeros(p.N)
         x, info = p.solve(b=zero, eps_rel=1e-8, max_it=100)  # r0 = 0: loop never entered, "converged"
         assert info["iterations"] == 0 and info["converged"] and np.all(x == 0)
@@ -182,15 +207,22 @@ def test_interrupt_flag(capi):
     with plan_for(capi, 128) as p:
         p.build_rhs()
         flag = ctypes.c_int(1)
-        x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, iters_per_graph=10, stop_flag=flag)
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, iters_per_graph=10, stop_flag=flag,
+                          small_grid_path=1)
         assert info["stop_reason"] == "INTERRUPTED" and not info["converged"]
         assert 0 < info["iterations"] <= 10
+        # cluster-resident kernel: the mapped flag is polled every 128 iterations
+        x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, stop_flag=flag, small_grid_path=2)
+        assert info["stop_reason"] == "INTERRUPTED" and not info["converged"] and info["cluster_path"] == 1
+        assert 0 < info["iterations"] <= 128
 
 
 # ---------------------------------------------------------------- MSGSolver rules (max-norm), both operators
-@pytest.mark.parametrize("op", [0, 1])
+@pytest.mark.parametrize("op", [0, 1, 2], ids=["matrix-free(cluster)", "csr", "matrix-free(graph)"])
 @pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1), (128, 0)])
 def test_maxnorm_rules_parity(capi, golden_ref, n, a_tag, op):
+    path = 1 if op == 2 else 0
+    op = 0 if op == 2 else op
     tag = f"grid_n{n}_a{a_tag}"
     eps = 1e-6 if n <= 30 else 1e-8
     with plan_for(capi, n, a_tag) as p:
@@ -201,7 +233,7 @@ def test_maxnorm_rules_parity(capi, golden_ref, n, a_tag, op):
             cb_ref = golden_ref[f"{tag}_msg_{cname}_cb"]
             got = []
             x, info = p.solve(b=golden_ref[tag + "_rhs"], u=golden_ref[tag + "_true"], op=op,
-                              rule=capi.RULE_MAXNORM, max_it=10000,
+                              rule=capi.RULE_MAXNORM, max_it=10000, small_grid_path=path,
                               callback=lambda it, pr, rs, er: got.append((it, pr, rs, er)), **kw)
             assert abs(info["iterations"] - int(info_ref[0])) <= 1
             assert info["converged"] == bool(info_ref[1])
