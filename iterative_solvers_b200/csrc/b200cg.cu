@@ -217,7 +217,9 @@ static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* ti
     for (size_t i = 0; i < all.size(); ++i) per_cta[i % grid].push_back(all[i]);
   } else {
     const int MIN_ROWS = 4;       // below this the two halo rows dominate
-    const int TILES_PER_CTA = 4;  // ranges per CTA when there is enough work
+    // ranges per CTA: every range costs two halo rows, so only long marches are split (4 x >= 128 rows)
+    int TILES_PER_CTA = (int)std::max<long long>(1, std::min<long long>(4, total / ((long long)max_grid * 128)));
+    if (const char* env = getenv("B200CG_TILES_PER_CTA")) TILES_PER_CTA = std::max(1, atoi(env));
     long long nranges = std::min<long long>((long long)max_grid * TILES_PER_CTA, std::max<long long>(1, total / MIN_ROWS));
     int grid = (int)std::min<long long>(max_grid, nranges);
     if (nranges > grid) nranges = (nranges / grid) * grid;  // same count for every CTA
