@@ -192,6 +192,10 @@ int b200cg_solve(b200cg_plan_t plan, const b200cg_params* params, const double* 
  * residual = A x - b and error = x - u: DirichletSolver::computeResidual / computeError
  * (dirichlet_solver.cpp:147-180). Either output may be NULL. op selects the stencil or the CSR matrix. */
 int b200cg_postprocess(b200cg_plan_t plan, int op, double* residual_host, double* error_host);
+/* Diagnostics: start/end time stamps (ns, device global timer) of every persistent CTA in the last launch of a sweep
+ * kernel flavour (0 = dot phase, 1 = update phase without x, 2 = update phase with x). out receives 2 * (*n_ctas)
+ * values; capacity is the number of pairs out can hold. */
+int b200cg_cta_times(b200cg_plan_t plan, int flavour, uint64_t* out, int capacity, int* n_ctas);
 /* copy the device-resident solution of the last solve (keep_x_on_device) to the host */
 int b200cg_get_solution(b200cg_plan_t plan, double* x_host);
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "b200cg_partition",
     "b200cg_build_rhs", "b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_coords",
     "b200cg_apply", "b200cg_set_csr", "b200cg_assemble_csr", "b200cg_get_csr", "b200cg_csr_apply",
-    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution",
+    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.b200cg_free_pinned.argtypes = [C.c_void_p]
         L.b200cg_comm_unique_id.argtypes = [C.c_void_p]
         L.b200cg_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.b200cg_cta_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -274,6 +275,14 @@ class Plan:
         check(self.L.b200cg_solve(self.h, C.byref(prm), _ptr(b), _ptr(u), _ptr(x_out), C.byref(info),
                                   C.cast(cb, C.c_void_p) if cb else None, None, flag_ptr))
         return x_out, info.as_dict()
+
+    def cta_times(self, flavour):
+        """(start_ns, end_ns) of every persistent CTA in the last launch of a sweep-kernel flavour (diagnostics)."""
+        cap = 1024
+        buf = np.zeros(2 * cap, dtype=np.uint64)
+        n = C.c_int()
+        check(self.L.b200cg_cta_times(self.h, int(flavour), _ptr(buf), cap, C.byref(n)))
+        return buf[: 2 * n.value].reshape(-1, 2).astype(np.int64)
 
     def postprocess(self, op=OP_MATRIX_FREE, want_residual=True, want_error=True):
         res = np.empty(self.n_local) if want_residual else None

@@ -58,17 +58,22 @@ struct GraphEntry {
   int kernels = 0;
 };
 
-struct TileTable {
+struct TileTable {  // one per sweep flavour: 0 = dot phase, 1 = update without x, 2 = everything else
   Tile* d_tiles = nullptr;
   int* d_cta_begin = nullptr;
+  size_t tile_capacity = 0;
+  int ctas_per_sm = 2;
   int grid = 0, n_tiles = 0;
+  bool balanced = false;       // feedback balancing applies (long marches)
+  std::vector<double> weight;  // relative share of the sweep per CTA
 };
 
 struct b200cg_plan_s {
   b200cg_plan_desc desc;
   Geom g;
   int sms = 148;
-  TileTable tile_tab[2];  // sweep work lists for 2 and 3 resident CTAs per SM
+  TileTable tile_tab[3];  // sweep work lists per flavour
+  int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int shape_dot = 3, shape_upd = 2, shape_nox = 3;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   bool cluster_enabled = true;                      // small-grid path allowed (B200CG_CLUSTER=0 disables)
@@ -88,6 +93,8 @@ struct b200cg_plan_s {
   CbRecord* d_log = nullptr;
   CbRecord* h_log = nullptr;  // pinned mirror
   int* h_stop = nullptr;      // mapped flag the cluster kernel polls (interrupt requests)
+  unsigned long long* d_clock[3] = {nullptr, nullptr, nullptr};  // per-CTA start/end stamps per sweep flavour
+  int clock_ctas[3] = {0, 0, 0};
   int* d_stop = nullptr;
   double* d_partials = nullptr;
   int partial_slots = 0;
@@ -187,12 +194,13 @@ static int setup_geometry(b200cg_plan_s* P) {
 }
 
 // Cuts the sweep over this rank's rows into tiles and deals them to the resident CTAs.
-// Default policy: linearise all (strip, row) pairs strip-major, cut the sequence into grid * TILES_PER_CTA
-// equal ranges (split where a range crosses a strip end) and give CTA c the ranges c, c + grid, ... - every
-// CTA gets the same number of rows to within one, and a tile's two halo rows are amortised over its height.
+// All (strip, row) pairs are linearised strip-major and cut into grid * tiles_per_cta ranges (split where a range
+// crosses a strip end); CTA c gets the ranges c, c + grid, ... . A range's length is proportional to the weight of
+// its CTA: 1 at first (equal split), then corrected from the measured per-CTA sweep times (rebalance_tiles) - SMs
+// differ by 10-15 % in achieved memory throughput on the write-heavy sweeps, and the pattern is stable from launch
+// to launch (profiles/r1_scheduling_experiments.md). A tile's two halo rows are amortised over its height.
 // desc.tile_rows > 0 forces fixed-height tiles instead (tests: ragged heights, many tiles per CTA).
-static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* tiles, std::vector<int>* cta_begin,
-                        int* grid_out) {
+static void build_tiles(b200cg_plan_s* P, TileTable* tt, std::vector<Tile>* tiles, std::vector<int>* cta_begin) {
   const Geom& g = P->g;
   struct Col { int col0, y0, y1, xlo; };
   std::vector<Col> cols;  // one entry per (block, strip)
@@ -205,8 +213,9 @@ static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* ti
     for (int s = 0; s < strips; ++s) cols.push_back({s * STRIP_OUT, yU0, yU1, 1});
   long long total = 0;
   for (const Col& c : cols) total += c.y1 - c.y0;
-  const int max_grid = P->sms * ctas_per_sm;
+  const int max_grid = P->sms * tt->ctas_per_sm;
   std::vector<std::vector<Tile>> per_cta;
+  tt->balanced = false;
   if (P->desc.tile_rows > 0) {
     std::vector<Tile> all;
     for (const Col& c : cols)
@@ -218,16 +227,25 @@ static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* ti
   } else {
     const int MIN_ROWS = 4;       // below this the two halo rows dominate
     // ranges per CTA: every range costs two halo rows, so only long marches are split (4 x >= 128 rows)
-    int TILES_PER_CTA = (int)std::max<long long>(1, std::min<long long>(4, total / ((long long)max_grid * 128)));
-    if (const char* env = getenv("B200CG_TILES_PER_CTA")) TILES_PER_CTA = std::max(1, atoi(env));
-    long long nranges = std::min<long long>((long long)max_grid * TILES_PER_CTA, std::max<long long>(1, total / MIN_ROWS));
-    int grid = (int)std::min<long long>(max_grid, nranges);
+    int tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(4, total / ((long long)max_grid * 128)));
+    if (const char* env = getenv("B200CG_TILES_PER_CTA")) tiles_per_cta = std::max(1, atoi(env));
+    long long nranges = std::min<long long>((long long)max_grid * tiles_per_cta, std::max<long long>(1, total / MIN_ROWS));
+    const int grid = (int)std::min<long long>(max_grid, nranges);
     if (nranges > grid) nranges = (nranges / grid) * grid;  // same count for every CTA
     per_cta.resize(std::max(grid, 1));
+    if ((int)tt->weight.size() != grid) tt->weight.assign(grid, 1.0);
+    tt->balanced = total / grid >= 64;  // worth balancing only when every CTA has a long march
+    // cumulative weight at the range boundaries -> boundaries in rows
+    double wsum = 0.0;
+    for (long long r = 0; r < nranges; ++r) wsum += tt->weight[r % grid];
     size_t ci = 0;
     long long pos = 0;  // linear position of cols[ci].y0
+    double wacc = 0.0;
+    long long lo = 0;
     for (long long r = 0; r < nranges; ++r) {
-      long long lo = total * r / nranges, hi = total * (r + 1) / nranges;
+      wacc += tt->weight[r % grid];
+      long long hi = (r + 1 == nranges) ? total : (long long)std::llround((double)total * (wacc / wsum));
+      hi = std::max(hi, lo);
       while (lo < hi) {
         while (ci < cols.size() && pos + (cols[ci].y1 - cols[ci].y0) <= lo) {
           pos += cols[ci].y1 - cols[ci].y0;
@@ -246,7 +264,53 @@ static void build_tiles(b200cg_plan_s* P, int ctas_per_sm, std::vector<Tile>* ti
     tiles->insert(tiles->end(), v.begin(), v.end());
     cta_begin->push_back((int)tiles->size());
   }
-  *grid_out = (int)per_cta.size();
+  tt->grid = (int)per_cta.size();
+  tt->n_tiles = (int)tiles->size();
+}
+
+// (Re)builds a flavour's tile table on the host and puts it into its device arrays (allocated once, with slack:
+// the graphs hold these pointers).
+static int upload_tiles(b200cg_plan_s* P, TileTable* tt) {
+  std::vector<Tile> tiles;
+  std::vector<int> cta_begin;
+  build_tiles(P, tt, &tiles, &cta_begin);
+  if (!tt->d_tiles) {
+    tt->tile_capacity = tiles.size() + 4 * ((size_t)(P->g.n - 1) / STRIP_OUT + 2) + 64;  // + strip-end splits
+    CU(cudaMalloc(&tt->d_tiles, tt->tile_capacity * sizeof(Tile)));
+    CU(cudaMalloc(&tt->d_cta_begin, ((size_t)P->sms * tt->ctas_per_sm + 1) * sizeof(int)));
+  }
+  if (tiles.size() > tt->tile_capacity) return fail(B200CG_ERR_STATE, "tile table overflow (%zu > %zu)", tiles.size(), tt->tile_capacity);
+  if (!tiles.empty()) CU(cudaMemcpy(tt->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(tt->d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return B200CG_OK;
+}
+
+// One feedback step: every CTA swept work proportional to its weight and took T_c; give it weight * (mean T / T_c)
+// (damped), so that all CTAs finish together. Called between graph launches while a plan is young.
+static int rebalance_tiles(b200cg_plan_s* P, int flavour) {
+  TileTable* tt = &P->tile_tab[flavour];
+  if (!tt->balanced || tt->grid <= 1) return B200CG_OK;
+  std::vector<unsigned long long> clk(2 * (size_t)tt->grid);
+  CU(cudaMemcpy(clk.data(), P->d_clock[flavour], clk.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (int c = 0; c < tt->grid; ++c) {
+    if (clk[2 * c] == 0 || clk[2 * c + 1] <= clk[2 * c]) return B200CG_OK;  // flavour did not run in this launch
+    t0 = std::min(t0, clk[2 * c]);
+  }
+  double mean = 0.0;
+  std::vector<double> T(tt->grid);
+  for (int c = 0; c < tt->grid; ++c) {
+    T[c] = (double)(clk[2 * c + 1] - t0);
+    mean += T[c] / tt->grid;
+  }
+  double wsum = 0.0;
+  for (int c = 0; c < tt->grid; ++c) {
+    const double f = std::min(1.25, std::max(0.8, mean / T[c]));
+    tt->weight[c] *= 1.0 + 0.8 * (f - 1.0);
+    wsum += tt->weight[c];
+  }
+  for (double& w : tt->weight) w *= tt->grid / wsum;
+  return upload_tiles(P, tt);
 }
 
 static int ew_grid(const b200cg_plan_s* P, long long work_items) {
@@ -316,6 +380,7 @@ static void free_plan(b200cg_plan_s* P) {
   if (P->h_state) cudaFreeHost(P->h_state);
   if (P->h_log) cudaFreeHost(P->h_log);
   if (P->h_stop) cudaFreeHost(P->h_stop);
+  for (auto& c : P->d_clock) cudaFree(c);
   for (auto& e : P->ev)
     if (e) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -362,20 +427,13 @@ static int plan_create_impl(b200cg_plan_s* P) {
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
+  for (auto& c : P->d_clock) {
+    CU(cudaMalloc(&c, sizeof(unsigned long long) * 2 * (size_t)P->sms * 3));
+    CU(cudaMemsetAsync(c, 0, sizeof(unsigned long long) * 2 * (size_t)P->sms * 3, P->stream));
+  }
   CU(cudaHostAlloc(&P->h_stop, sizeof(int), cudaHostAllocMapped));
   *P->h_stop = 0;
   CU(cudaHostGetDevicePointer(&P->d_stop, P->h_stop, 0));
-  for (int t = 0; t < 2 && !P->generic; ++t) {
-    std::vector<Tile> tiles;
-    std::vector<int> cta_begin;
-    TileTable& tt = P->tile_tab[t];
-    build_tiles(P, 2 + t, &tiles, &cta_begin, &tt.grid);
-    tt.n_tiles = (int)tiles.size();
-    CU(cudaMalloc(&tt.d_tiles, std::max<size_t>(tiles.size(), 1) * sizeof(Tile)));
-    CU(cudaMalloc(&tt.d_cta_begin, cta_begin.size() * sizeof(int)));
-    if (!tiles.empty()) CU(cudaMemcpy(tt.d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(tt.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-  }
   {
     auto env_int = [](const char* name, int dflt) {
       const char* v = getenv(name);
@@ -385,6 +443,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
+    P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->cluster_enabled = env_int("B200CG_CLUSTER", 1) != 0;
     if (!P->generic && P->cluster_enabled) {
       // probe once whether the non-portable 16-CTA cluster is schedulable with a full shared-memory carve-out
@@ -406,6 +465,15 @@ static int plan_create_impl(b200cg_plan_s* P) {
         P->cluster16_ok = nclusters > 0;
       cudaGetLastError();
     }
+  }
+  if (!P->generic) {
+    // resident CTAs per SM of each flavour's launch shape (ShapeOf<>::CTAS)
+    auto ctas_of = [](int shape) { return (shape == 1 || shape == 3) ? 3 : 2; };
+    P->tile_tab[0].ctas_per_sm = ctas_of(P->shape_dot);
+    P->tile_tab[1].ctas_per_sm = ctas_of(P->shape_nox);
+    P->tile_tab[2].ctas_per_sm = 2;  // every other flavour runs a 2-CTAs/SM shape
+    if (P->shape_upd == 1) P->shape_upd = 0;
+    for (auto& tt : P->tile_tab) RET(upload_tiles(P, &tt));
   }
   P->partial_slots = P->sms * 16 + 64;
   CU(cudaMalloc(&P->d_partials, sizeof(double) * MAX_PARTIALS * (size_t)P->partial_slots));
@@ -605,10 +673,16 @@ static int launch_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = true;
   }
-  const TileTable& tt = P->tile_tab[Sh::CTAS - 2];
+  // flavour: 0 = dot phase, 1 = update without x (NOX), 2 = everything else (its table is cut for 2 CTAs/SM)
+  constexpr int fl = (MODE == MODE_DOT && FLAGS == 0) ? 0 : ((MODE == MODE_UPD && FLAGS == F_NOX) ? 1 : 2);
+  const TileTable& tt = P->tile_tab[fl];
   if (tt.n_tiles <= 0) return B200CG_OK;
   a.tiles = tt.d_tiles;
   a.cta_begin = tt.d_cta_begin;
+  // only the three hot kernels stamp their CTAs (flavour 2 = the x-touching update of the default path)
+  constexpr bool stamped = fl < 2 || (MODE == MODE_UPD && (FLAGS == F_X2 || FLAGS == 0));
+  a.cta_clock = stamped ? P->d_clock[fl] : nullptr;
+  if (stamped) P->clock_ctas[fl] = tt.grid;
   kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
@@ -964,8 +1038,9 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   unsigned int consumed = 0;
   bool interrupted = false;
   double dot_ms = 0.0, upd_even = 0.0, upd_odd = 0.0;
-  int samples = 0, it_before = 0;
+  int samples = 0, it_before = 0, it_launch0 = 0;
   (void)it_before;
+  (void)it_launch0;
   if (use_cluster) {
     *P->h_stop = 0;
     CU(cudaEventRecord(P->ev[5], s));
@@ -1069,6 +1144,12 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
       }
       if (consumed == 0) consumed = 1;
       if (st.done) break;
+      if (P->balance_rounds > 0 && !csr && st.it - it_launch0 >= 2) {
+        // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
+        for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
+        --P->balance_rounds;
+      }
+      it_launch0 = st.it;
       if (stop_flag && *stop_flag) {
         interrupted = true;
         break;
@@ -1181,5 +1262,16 @@ extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host
     }
   }
   CU(cudaStreamSynchronize(s));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_cta_times(b200cg_plan_t P, int flavour, uint64_t* out, int capacity, int* n_ctas) {
+  if (!P || !out || !n_ctas) return fail(B200CG_ERR_INVALID_ARG, "plan/out/n_ctas is NULL");
+  if (flavour < 0 || flavour > 2) return fail(B200CG_ERR_INVALID_ARG, "flavour %d outside [0, 2]", flavour);
+  NEED_GEOMETRY(P);
+  const int n = std::min(P->clock_ctas[flavour], capacity);
+  CU(cudaSetDevice(P->desc.device));
+  CU(cudaMemcpy(out, P->d_clock[flavour], sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+  *n_ctas = n;
   return B200CG_OK;
 }

@@ -40,10 +40,16 @@ struct TileArgs {
   const Tile* tiles;      // tile table, grouped per CTA
   const int* cta_begin;   // [gridDim.x + 1] offsets into tiles
   int defer;           // sharded plan: publish this rank's totals in st->loc_*, finalize after the all-reduce
+  unsigned long long* cta_clock;  // [2 * gridDim.x] globaltimer at CTA start / end of its sweep (load balancing)
   Geom g;
 };
 
 // --------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ double2 ld_ro2(const double* p, bool ok) {
   // read-only for the lifetime of the kernel: non-coherent path
   return ok ? __ldg(reinterpret_cast<const double2*>(p)) : make_double2(0.0, 0.0);

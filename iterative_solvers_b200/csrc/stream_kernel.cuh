@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
       mbar_init(&empty[i], CONS_WARPS);
     }
     mbar_fence_init();
+    if (a.cta_clock) a.cta_clock[2 * blockIdx.x] = global_ns();
   }
   __syncthreads();
 
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
     }
   }
 
+  // end of this CTA's sweep: the first consumer warp is as good a witness as any (all finish within a stage)
+  if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
   if (NS + NM == 0) return;
   if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
   // ---- one thread: turn the totals into the next scalars
