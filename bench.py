@@ -249,7 +249,7 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, dot_ms, upd_ms, samples, its_done = 0.0, 0, 0.0, 0.0, 0, 0
-    upd_even_ms, upd_odd_ms, xdefer = 0.0, 0.0, 0
+    upd_even_ms, upd_odd_ms, xdefer, peer_exchange = 0.0, 0.0, 0, 0
     for _ in range(args.steps):
         _, info = plan.solve(rhs_on_device=True, keep_x_on_device=True, **solve_kw)
         dev_ms += info["device_ms"]
@@ -261,6 +261,7 @@ def run_b200(args):
             upd_even_ms += info["upd_even_ms"]
             upd_odd_ms += info["upd_odd_ms"]
             xdefer = info["x_deferral"]
+            peer_exchange = info["peer_exchange"]
             samples += 1
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -341,7 +342,8 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, args.iters, args.domain, args.op), "grid_n": n, "unknowns": plan.N,
                    "unknowns_per_gpu": plan.N / world, "iterations_per_step": args.iters,
-                   "parallelism": f"row-slab x{world}" if world > 1 else "single GPU",
+                   "parallelism": (f"row-slab x{world}, " + ("NVLink peer-memory halo + reductions" if peer_exchange
+                                                            else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "inputs_exceed_l2" if n_local * 8 > 200e6 else "inputs_fit_l2_no_flush",
                    "timing": "CUDA events on the library's solve stream, summed over steps, max over ranks",
                    "wall_ms_per_step": wall_ms / max(args.steps, 1)},

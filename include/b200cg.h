@@ -125,7 +125,9 @@ typedef struct {
   double upd_odd_ms;       /* no report) even iterations skip x (32 B/unknown) and odd ones carry both (48 B)    */
   int x_deferral;          /* 1 if this solve touched x only every other iteration */
   int cluster_path;        /* 1 if this solve ran as one cluster-resident kernel (small_grid_path) */
-  int reserved[4];
+  int peer_exchange;       /* sharded plans: 1 if halo rows and reductions went over NVLink peer memory (CUDA IPC),
+                              0 if over NCCL send/recv + all-reduce */
+  int reserved[3];
 } b200cg_info;
 
 /* (iteration, precision, residual, error) - Solver::setIterationCallback, solver.hpp:46-50. Called on the

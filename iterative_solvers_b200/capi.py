@@ -54,7 +54,7 @@ class SolveInfo(C.Structure):
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("dot_kernel_ms", C.c_double),
                 ("upd_kernel_ms", C.c_double), ("kernel_samples", C.c_int), ("local_unknowns", C.c_int64),
                 ("upd_even_ms", C.c_double), ("upd_odd_ms", C.c_double), ("x_deferral", C.c_int),
-                ("cluster_path", C.c_int), ("reserved", C.c_int * 4)]
+                ("cluster_path", C.c_int), ("peer_exchange", C.c_int), ("reserved", C.c_int * 3)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -105,6 +105,16 @@ struct b200cg_plan_s {
   std::map<int, GraphEntry> graphs;
   CsrData csr;
   Comm comm;
+  // NVLink peer-memory exchange (sharded plans): IPC-mapped neighbour vectors and every rank's PeerSync block
+  bool peer_mode = false;
+  PeerSync* d_sync = nullptr;        // this rank's block
+  PeerLinks* d_links = nullptr;      // device table of all ranks' blocks
+  std::vector<void*> ipc_opened;     // everything cudaIpcOpenMemHandle returned (closed at destroy)
+  double* nb_below_r[2] = {nullptr, nullptr};  // neighbour vectors (base pointers of its pitched buffers)
+  double* nb_below_p[2] = {nullptr, nullptr};
+  double* nb_above_r[2] = {nullptr, nullptr};
+  double* nb_above_p[2] = {nullptr, nullptr};
+  unsigned long long peer_epoch[2] = {0, 0};
   int64_t n_global = 0;
   std::vector<int> ycuts;  // row cuts of all ranks
 };
@@ -352,12 +362,86 @@ extern "C" int b200cg_comm_unique_id(void* id128) {
   return B200CG_OK;
 }
 
+// Peer-memory exchange: swap CUDA IPC handles of r[2], p[2] and the PeerSync block over NCCL (once), map the two
+// neighbours' vectors and every rank's block. All ranks then agree (min-reduction) whether the mapping worked
+// everywhere; otherwise the plan keeps the NCCL path. B200CG_PEER=0 forces the NCCL path.
+static int setup_peer_memory(b200cg_plan_s* P) {
+  const int world = P->desc.world, rank = P->desc.rank;
+  std::string err;
+  bool mine = true;
+  {
+    const char* env = getenv("B200CG_PEER");
+    if ((env && atoi(env) == 0) || world > PEER_MAX_RANKS) mine = false;
+  }
+  CU(cudaMalloc(&P->d_sync, sizeof(PeerSync)));
+  CU(cudaMemset(P->d_sync, 0, sizeof(PeerSync)));
+  constexpr int NH = 5;  // handles per rank: r0, r1, p0, p1, sync
+  std::vector<cudaIpcMemHandle_t> all((size_t)world * NH);
+  {
+    cudaIpcMemHandle_t h[NH];
+    void* ptrs[NH] = {P->r[0], P->r[1], P->p[0], P->p[1], P->d_sync};
+    for (int k = 0; k < NH; ++k)
+      if (cudaIpcGetMemHandle(&h[k], ptrs[k]) != cudaSuccess) {
+        mine = false;
+        memset(&h[k], 0, sizeof(h[k]));
+        cudaGetLastError();
+      }
+    unsigned char *d_send = nullptr, *d_recv = nullptr;
+    CU(cudaMalloc(&d_send, sizeof(h)));
+    CU(cudaMalloc(&d_recv, sizeof(h) * world));
+    CU(cudaMemcpyAsync(d_send, h, sizeof(h), cudaMemcpyHostToDevice, P->stream));
+    if (!comm_allgather_bytes(&P->comm, d_send, d_recv, sizeof(h), P->stream, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+    CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(h) * world, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    cudaFree(d_send);
+    cudaFree(d_recv);
+  }
+  PeerLinks links;
+  memset(&links, 0, sizeof(links));
+  links.rank = rank;
+  links.world = world;
+  auto open = [&](int r, int k) -> void* {
+    void* q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, all[(size_t)r * NH + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      mine = false;
+      return nullptr;
+    }
+    P->ipc_opened.push_back(q);
+    return q;
+  };
+  if (mine) {
+    for (int r = 0; r < world && mine; ++r) links.sync[r] = (r == rank) ? P->d_sync : static_cast<PeerSync*>(open(r, 4));
+    if (rank > 0)
+      for (int k = 0; k < 2 && mine; ++k) {
+        P->nb_below_r[k] = static_cast<double*>(open(rank - 1, k));
+        P->nb_below_p[k] = static_cast<double*>(open(rank - 1, 2 + k));
+      }
+    if (rank + 1 < world)
+      for (int k = 0; k < 2 && mine; ++k) {
+        P->nb_above_r[k] = static_cast<double*>(open(rank + 1, k));
+        P->nb_above_p[k] = static_cast<double*>(open(rank + 1, 2 + k));
+      }
+  }
+  bool all_ok = false;
+  if (!comm_all_agree(&P->comm, mine, &all_ok, P->stream, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  P->peer_mode = all_ok;
+  if (all_ok) {
+    CU(cudaMalloc(&P->d_links, sizeof(PeerLinks)));
+    CU(cudaMemcpy(P->d_links, &links, sizeof(links), cudaMemcpyHostToDevice));
+  }
+  return B200CG_OK;
+}
+
 // ------------------------------------------------------------------------------------------- plan API
 static void free_plan(b200cg_plan_s* P) {
   if (!P) return;
   cudaSetDevice(P->desc.device);
   for (auto& kv : P->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (void* q : P->ipc_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(P->d_sync);
+  cudaFree(P->d_links);
   comm_destroy(&P->comm);
   csr_free(&P->csr);
   for (int i = 0; i < 2; ++i) {
@@ -482,6 +566,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     if (!P->desc.comm_id) return fail(B200CG_ERR_INVALID_ARG, "world > 1 needs comm_id (b200cg_comm_unique_id)");
     if (!comm_init(&P->comm, P->desc.comm_id, P->desc.rank, P->desc.world, P->stream, &err))
       return fail(B200CG_ERR_COMM, "%s", err.c_str());
+    RET(setup_peer_memory(P));
   }
   CU(cudaStreamSynchronize(P->stream));
   return B200CG_OK;
@@ -714,7 +799,7 @@ static TileArgs base_args(b200cg_plan_s* P) {
   a.st = P->d_state;
   a.partials = P->d_partials;
   a.cb_log = P->d_log;
-  a.defer = P->desc.world > 1 ? 1 : 0;
+  a.defer = P->desc.world > 1 ? 1 : 0;  // build_graph switches the loop kernels to 2 (peer memory) when it can
   a.g = P->g;
   return a;
 }
@@ -832,9 +917,30 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     a.p_out = P->p[par ^ 1];
     a.u = P->u;
     const int fl = xdefer ? ((k & 1) ? F_X2 : F_NOX) : ((with_u ? F_U : 0) | (report ? F_REPORT : 0));
+    // sharded plans: reductions and halo rows over NVLink peer memory (no NCCL call in the loop); the per-iteration
+    // report variant keeps the NCCL exchange
+    const bool peer = P->desc.world > 1 && P->peer_mode && !report;
+    if (peer) {
+      a.defer = 2;
+      a.peers = P->d_links;
+      const Geom& g = P->g;
+      const int rank = P->desc.rank;
+      if (rank > 0) {  // neighbour below: its top halo row is its last stored row
+        const size_t rows_below = (size_t)(P->ycuts[rank] - P->ycuts[rank - 1]) + 2;
+        a.nb_r_below = P->nb_below_r[par ^ 1] + (rows_below - 1) * g.pitch;
+        a.nb_p_below = P->nb_below_p[par ^ 1] + (rows_below - 1) * g.pitch;
+      }
+      if (rank + 1 < P->desc.world) {  // neighbour above: its bottom halo row is its stored row 0
+        a.nb_r_above = P->nb_above_r[par ^ 1];
+        a.nb_p_above = P->nb_above_p[par ^ 1];
+      }
+    }
     rc = launch_tile<MODE_DOT, 0>(P, a, s);
     ++kernels;
-    if (rc == B200CG_OK && P->desc.world > 1) {
+    if (rc == B200CG_OK && peer) {
+      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 1, fl);
+      ++kernels;
+    } else if (rc == B200CG_OK && P->desc.world > 1) {
       rc = reduce_and_finalize(P, 1, fl, false, s);
       ++kernels;
     }
@@ -847,7 +953,10 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     else if (with_u) rc = launch_tile<MODE_UPD, F_U>(P, a, s);
     else rc = launch_tile<MODE_UPD, 0>(P, a, s);
     ++kernels;
-    if (rc == B200CG_OK && P->desc.world > 1) {
+    if (rc == B200CG_OK && peer) {
+      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 2, fl);
+      ++kernels;
+    } else if (rc == B200CG_OK && P->desc.world > 1) {
       rc = reduce_and_finalize(P, 2, fl, /*with_max=*/!xdefer, s);
       ++kernels;
       if (rc == B200CG_OK) rc = exchange_halo2(P, P->r[par ^ 1], P->p[par ^ 1]);
@@ -1016,6 +1125,8 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   hs.rule = prm->rule;
   hs.has_u = with_u ? 1 : 0;
   hs.callback_every = (cb && prm->rule == B200CG_RULE_MAXNORM) ? (prm->callback_every > 0 ? prm->callback_every : 100) : 0;
+  hs.epoch[0] = P->peer_epoch[0];  // the PeerSync flags are monotonic over the plan's life
+  hs.epoch[1] = P->peer_epoch[1];
   *P->h_state = hs;
   CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
 
@@ -1160,6 +1271,9 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
 
   // ---- outputs
   const DevState st = *P->h_state;
+  P->peer_epoch[0] = st.epoch[0];
+  P->peer_epoch[1] = st.epoch[1];
+  if (st.comm_error) return fail(B200CG_ERR_COMM, "peer-memory exchange timed out after %d iterations (a rank stopped publishing)", st.it);
   if (xdefer && st.x_pending) {  // the loop ended on an even iteration: settle x += alpha * p
     const Geom& g = P->g;
     const size_t begin = (size_t)(g.ylo - g.ybase) * g.pitch, count = (size_t)(g.yhi - g.ylo) * g.pitch;
@@ -1204,6 +1318,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   info->upd_odd_ms = samples ? upd_odd / samples : 0.0;
   info->x_deferral = xdefer ? 1 : 0;
   info->cluster_path = use_cluster ? 1 : 0;
+  info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !report && !use_cluster) ? 1 : 0;
   info->kernel_samples = samples;
   // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
   if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);

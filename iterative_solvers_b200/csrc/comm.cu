@@ -15,6 +15,7 @@ struct Api {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -46,6 +47,7 @@ bool load_api(std::string* err) {
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart");
@@ -139,6 +141,28 @@ bool comm_allreduce_state(Comm* c, DevState* st, bool with_max, cudaStream_t s, 
   if (ok && with_max) ok = check(g_api.AllReduce(maxs, maxs, 4, ncclDouble, ncclMax, comm, s), "ncclAllReduce(max)", err);
   ncclResult_t r = g_api.GroupEnd();
   return ok && check(r, "ncclGroupEnd", err);
+}
+
+bool comm_allgather_bytes(Comm* c, const void* send_dev, void* recv_dev, size_t bytes, cudaStream_t s, std::string* err) {
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  return check(g_api.AllGather(send_dev, recv_dev, bytes, ncclUint8, comm, s), "ncclAllGather", err);
+}
+
+bool comm_all_agree(Comm* c, bool mine, bool* all, cudaStream_t s, std::string* err) {
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  int* d = nullptr;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) {
+    *err = "cudaMalloc failed in comm_all_agree";
+    return false;
+  }
+  int h = mine ? 1 : 0;
+  cudaMemcpyAsync(d, &h, sizeof(int), cudaMemcpyHostToDevice, s);
+  bool ok = check(g_api.AllReduce(d, d, 1, ncclInt32, ncclMin, comm, s), "ncclAllReduce(min)", err);
+  cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  cudaFree(d);
+  *all = h != 0;
+  return ok;
 }
 
 }  // namespace b200cg

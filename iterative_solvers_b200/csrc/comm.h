@@ -26,4 +26,9 @@ bool comm_halo2(Comm* c, double* v0, double* v1, int yrows, int pitch, cudaStrea
 // in-place all-reduce of st->loc_s (sum, 4 doubles) and optionally st->loc_m (max, 4 doubles)
 bool comm_allreduce_state(Comm* c, DevState* st, bool with_max, cudaStream_t s, std::string* err);
 
+// all-gather of `bytes` per rank (device buffers); used once, to swap CUDA IPC handles
+bool comm_allgather_bytes(Comm* c, const void* send_dev, void* recv_dev, size_t bytes, cudaStream_t s, std::string* err);
+// all ranks learn whether every rank said yes (min-reduction of a flag; host values, blocking)
+bool comm_all_agree(Comm* c, bool mine, bool* all, cudaStream_t s, std::string* err);
+
 }  // namespace b200cg

@@ -66,8 +66,26 @@ struct DevState {
   int stop_reason;
   unsigned int ticket;
   unsigned int n_log; // callback records appended so far
+  unsigned long long epoch[2];  // peer-memory exchange: publications consumed so far per phase
+  int comm_error;     // a peer flag did not arrive in time
+  int pad_comm;
   int report_pending; // MatrixFreeSolver callback: the update phase asks the report kernel to run
   int x_pending;      // x-deferral: the last iteration did not touch x; x += alpha_prev * p is owed
+};
+
+// ---- NVLink peer-memory exchange of the sharded plans (one process per GPU, buffers shared through CUDA IPC) ----
+// Every rank owns one PeerSync block; every rank's sweep kernels write their reduction partials straight into
+// all ranks' blocks (remote stores over NVLink) and then raise a flag with the epoch number; the finalize kernel
+// of each rank waits for all flags of the epoch and sums the slots in rank order (same result on every rank).
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_VALS = 8;  // [s0 s1 s2 s3 | m0 m1 m2 m3]
+struct PeerSync {
+  double vals[2][PEER_MAX_RANKS][PEER_VALS];        // [phase: 0 = dot, 1 = update][source rank]
+  unsigned long long flag[2][PEER_MAX_RANKS];       // epoch of the last complete publication
+};
+struct PeerLinks {                                  // device-resident table of mapped peer pointers
+  PeerSync* sync[PEER_MAX_RANKS];                   // every rank's block (own one included)
+  int rank, world;
 };
 
 struct CbRecord {

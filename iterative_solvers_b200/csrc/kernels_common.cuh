@@ -39,7 +39,14 @@ struct TileArgs {
   CbRecord* cb_log;
   const Tile* tiles;      // tile table, grouped per CTA
   const int* cta_begin;   // [gridDim.x + 1] offsets into tiles
-  int defer;           // sharded plan: publish this rank's totals in st->loc_*, finalize after the all-reduce
+  int defer;           // sharded plan: 1 = leave this rank's totals in st->loc_* for the NCCL all-reduce,
+                       // 2 = publish them into every rank's PeerSync block over NVLink (peer-memory path)
+  const PeerLinks* peers;  // defer == 2
+  // peer-memory halo: UPD writes its first / last owned row of r' and p straight into the neighbours' halo rows
+  double* nb_r_below;  // neighbour below: start of its top halo row in r_out (null: no neighbour / NCCL path)
+  double* nb_p_below;
+  double* nb_r_above;  // neighbour above: start of its bottom halo row
+  double* nb_p_above;
   unsigned long long* cta_clock;  // [2 * gridDim.x] globaltimer at CTA start / end of its sweep (load balancing)
   Geom g;
 };
@@ -172,6 +179,24 @@ __device__ __forceinline__ void finalize_report(DevState* st, CbRecord* log, dou
   if (has_u) st->err_l2 = sqrt(err2);
   append_record(st, log, (double)(st->it - 1), st->dx_l2, st->res_l2, st->err_l2);
   st->report_pending = 0;
+}
+
+// Peer-memory publication of a sweep kernel's totals (thread 0 of the last CTA): values first, then - after a
+// system-scope fence - the epoch flag, into every rank's PeerSync block.
+template <int NS, int NM>
+__device__ __forceinline__ void peer_publish(const PeerLinks* pl, DevState* st, int phase, const double (&s)[NS > 0 ? NS : 1],
+                                             const double (&mx)[NM > 0 ? NM : 1]) {
+  const unsigned long long epoch = st->epoch[phase] + 1ull;
+  for (int dst = 0; dst < pl->world; ++dst) {
+    double* v = pl->sync[dst]->vals[phase][pl->rank];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = k < NS ? s[k < NS ? k : 0] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[4 + k] = k < NM ? mx[k < NM ? k : 0] : 0.0;
+  }
+  __threadfence_system();
+  for (int dst = 0; dst < pl->world; ++dst)
+    *reinterpret_cast<volatile unsigned long long*>(&pl->sync[dst]->flag[phase][pl->rank]) = epoch;
 }
 
 // x-deferral bookkeeping after an update phase: a NOX iteration leaves x += alpha*p pending.

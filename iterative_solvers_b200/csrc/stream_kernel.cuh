@@ -288,6 +288,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
               if (!NOX) st2_out(a.x + eoff, xn);
               st2_out(a.r_out + eoff, rn);
               st2_out(a.p_out + eoff, make_double2(p0, p1));
+              // peer-memory halo: the slab's first / last row also lands in the neighbour's halo row (NVLink stores)
+              const int ye = y - 1;
+              const int cs = m.col0 + c2;
+              if (a.nb_r_below && ye == g.ylo) {
+                st2(a.nb_r_below + cs, rn);
+                st2(a.nb_p_below + cs, make_double2(p0, p1));
+              }
+              if (a.nb_r_above && ye == g.yhi - 1) {
+                st2(a.nb_r_above + cs, rn);
+                st2(a.nb_p_above + cs, make_double2(p0, p1));
+              }
             }
             acc_s[0] = fma(rn.x, rn.x, acc_s[0]);
             acc_s[0] = fma(rn.y, rn.y, acc_s[0]);
@@ -351,9 +362,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
 
   // end of this CTA's sweep: the first consumer warp is as good a witness as any (all finish within a stage)
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
+  if (MODE == MODE_UPD && a.defer == 2) __threadfence_system();  // remote halo stores before the exit ticket
   if (NS + NM == 0) return;
   if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
   // ---- one thread: turn the totals into the next scalars
+  if (a.defer == 2) {
+    peer_publish<NS, NM>(a.peers, st, MODE == MODE_DOT ? 0 : 1, acc_s, acc_m);
+    return;
+  }
   if (a.defer) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -66,7 +66,8 @@ def main():
                 got = np.array(got_cb)
                 ok = ok and len(got) == len(ref["hist"]) and np.all(
                     np.abs(got[:, 1:] - ref["hist"]) <= 1e-9 * np.max(np.abs(ref["hist"]), axis=0) + 1e-9 * np.abs(ref["hist"]))
-            print(f"[multigpu] n={n} domain={domain} {kind}: iterations {info['iterations']} vs {ref['iterations']}, "
+            print(f"[multigpu] n={n} domain={domain} {kind} (peer_exchange={info['peer_exchange']}): "
+                  f"iterations {info['iterations']} vs {ref['iterations']}, "
                   f"max rel diff {rel:.2e} -> {'ok' if ok else 'FAIL'}", flush=True)
             if not ok:
                 failures.append((n, domain, kind))
