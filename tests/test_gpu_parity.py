@@ -386,3 +386,56 @@ def test_full_size_operator_properties(capi):
         res, _ = p.postprocess(want_error=False)  # A x - b recomputed
         assert abs(np.linalg.norm(res) - info["r_l2"]) <= 1e-8 * info["r0_l2"]
         assert np.max(np.abs(res + (b - p.apply(xs)))) <= 1e-12 * np.max(np.abs(b))
+
+
+# ---------------------------------------------------------------- execution-strategy knobs must not change the answer
+def _solve_with_env(capi, env, n, iters, **solve_kw):
+    import os
+
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        with plan_for(capi, n) as p:  # the knobs are read when the plan is created
+            p.build_rhs()
+            return p.solve(rhs_on_device=True, eps_rel=0.0, max_it=iters, **solve_kw)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_x_deferral_is_bit_identical(capi):
+    """x touched every other iteration (default on the relative-residual path) vs every iteration: the same additions in
+    the same order, so with the same fixed work split (same launch shape for both update flavours, no balancing) the
+    solutions are bit-identical - for odd and even iteration counts."""
+    common = {"B200CG_BALANCE": "0", "B200CG_SHAPE_NOX": "2", "B200CG_SHAPE_UPD": "2"}
+    for iters in (7, 40):
+        xa, ia = _solve_with_env(capi, dict(common, B200CG_XDEFER="1"), 2048, iters)
+        xb, ib = _solve_with_env(capi, dict(common, B200CG_XDEFER="0"), 2048, iters)
+        assert ia["x_deferral"] == 1 and ib["x_deferral"] == 0
+        assert ia["iterations"] == ib["iterations"] == iters
+        assert np.array_equal(xa, xb)
+        assert ia["r_l2"] == ib["r_l2"]
+
+
+def test_feedback_balancing_changes_only_the_summation_order(capi):
+    """The work split is re-cut from measured per-CTA times during the first graph launches; iterates may then differ
+    from the fixed split only by dot-product rounding."""
+    xa, ia = _solve_with_env(capi, {"B200CG_BALANCE": "4"}, 4096, 120, iters_per_graph=20)
+    xb, ib = _solve_with_env(capi, {"B200CG_BALANCE": "0"}, 4096, 120, iters_per_graph=20)
+    assert ia["iterations"] == ib["iterations"] == 120
+    assert relmax(xa, xb) < 1e-12
+    assert abs(ia["r_l2"] - ib["r_l2"]) <= 1e-12 * ib["r_l2"]
+    # fixed split: reproducible bit for bit from run to run
+    xc, ic = _solve_with_env(capi, {"B200CG_BALANCE": "0"}, 4096, 120, iters_per_graph=20)
+    assert np.array_equal(xb, xc) and ib["r_l2"] == ic["r_l2"]
+
+
+def test_launch_shapes_do_not_change_the_answer(capi):
+    ref, _ = _solve_with_env(capi, {"B200CG_BALANCE": "0"}, 1536, 30)
+    for dot, upd, nox in [(0, 0, 0), (1, 0, 1), (2, 2, 2), (3, 2, 3)]:
+        x, info = _solve_with_env(capi, {"B200CG_BALANCE": "0", "B200CG_SHAPE_DOT": str(dot), "B200CG_SHAPE_UPD": str(upd),
+                                         "B200CG_SHAPE_NOX": str(nox)}, 1536, 30)
+        assert info["iterations"] == 30 and relmax(x, ref) < 1e-12
