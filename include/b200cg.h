@@ -40,8 +40,11 @@ typedef enum {
                                (grid_system.cpp:17-43); requires even n == m (the reference numbering is
                                only self-consistent there, grid_system.cpp:103-111) */
   B200CG_DOMAIN_RECT = 1,   /* full rectangle, any n, m >= 2 (no reference counterpart; synthetic configs) */
-  B200CG_DOMAIN_GENERIC = 2 /* no geometry: a plan of generic_rows unknowns that only serves the CSR entry points
+  B200CG_DOMAIN_GENERIC = 2, /* no geometry: a plan of generic_rows unknowns that only serves the CSR entry points
                                (MSGSolver receives just a matrix and a rhs, msg_solver.hpp:50-53) */
+  B200CG_DOMAIN_LSHAPE_ANY = 3 /* the L-shaped region for any n, m >= 4 with the reference's numbering defects repaired
+                               (block B is n-1-n/2 wide, block U counted from m/2): identical to LSHAPE for even
+                               n == m, defined where the reference builds a malformed system */
 } b200cg_domain;
 
 typedef enum {

@@ -9,7 +9,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200CG_LIB", os.path.join(PKG, "libb200cg.so"))
 
-DOMAIN_LSHAPE, DOMAIN_RECT, DOMAIN_GENERIC = 0, 1, 2
+DOMAIN_LSHAPE, DOMAIN_RECT, DOMAIN_GENERIC, DOMAIN_LSHAPE_ANY = 0, 1, 2, 3
 OP_MATRIX_FREE, OP_CSR = 0, 1
 RULE_REL_L2, RULE_MAXNORM = 0, 1
 STOP_NAMES = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]

@@ -144,6 +144,8 @@ static int setup_geometry(b200cg_plan_s* P) {
                   "L-shaped domain needs even n == m >= 4 (got n=%d, m=%d): the reference numbering "
                   "(grid_system.cpp:103-111) is only self-consistent there",
                   d.n, d.m);
+  } else if (d.domain == B200CG_DOMAIN_LSHAPE_ANY) {
+    if (d.n < 4 || d.m < 4) return fail(B200CG_ERR_INVALID_ARG, "L-shaped domain needs n, m >= 4");
   } else if (d.domain == B200CG_DOMAIN_RECT) {
     if (d.n < 2 || d.m < 2) return fail(B200CG_ERR_INVALID_ARG, "RECT domain needs n, m >= 2");
   } else {
@@ -159,10 +161,10 @@ static int setup_geometry(b200cg_plan_s* P) {
   g.A = -2 * (1 / (g.hx * g.hx) + 1 / (g.hy * g.hy));
   g.xk = 1 / (g.hx * g.hx);
   g.yk = 1 / (g.hy * g.hy);
-  if (d.domain == B200CG_DOMAIN_LSHAPE) {
+  if (d.domain == B200CG_DOMAIN_LSHAPE || d.domain == B200CG_DOMAIN_LSHAPE_ANY) {
     g.xsplit = d.n / 2;
     g.ysplit = d.m / 2;
-    g.wB = d.n / 2 - 1;
+    g.wB = d.n - 1 - d.n / 2;  // = n/2 - 1 for even n (grid_system.cpp:108-111)
     g.wU = d.n - 1;
     g.NB = (long long)g.wB * (d.m / 2);
   } else {

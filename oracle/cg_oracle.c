@@ -32,6 +32,10 @@ int cgo_grid_init(cgo_grid* g, int m, int n, double a, double b, double c, doubl
     /* calculate_position_in_upper_area uses n/2 where m/2 is meant and the bottom-block width n/2-1
      * is only right for even n (grid_system.cpp:103-111): the numbering is self-consistent only for even n == m. */
     if (n != m || (n % 2) != 0 || n < 4) return -1;
+  } else if (kind == CGO_LSHAPE_ANY) {
+    /* the same region for any n, m >= 4 with the defects repaired: block B is n-1-n/2 wide,
+     * block U rows are counted from m/2. Identical to CGO_LSHAPE for even n == m; no reference counterpart otherwise. */
+    if (n < 4 || m < 4) return -1;
   } else {
     if (n < 2 || m < 2) return -1;
   }
@@ -65,6 +69,11 @@ int cgo_is_unknown(const cgo_grid* g, int x, int y) {
 long cgo_index(const cgo_grid* g, int x, int y) {
   if (!cgo_is_unknown(g, x, y)) return -1;
   if (g->kind == CGO_RECT) return (long)(y - 1) * (g->n - 1) + (x - 1);
+  if (g->kind == CGO_LSHAPE_ANY) {
+    const long wB = g->n - 1 - g->n / 2;
+    if (y <= g->m / 2) return wB * (y - 1) + x - g->n / 2 - 1;
+    return wB * (g->m / 2) + (long)(y - g->m / 2 - 1) * (g->n - 1) + x - 1;
+  }
   if (y <= g->m / 2) return (long)(g->n / 2 - 1) * (y - 1) + x - g->n / 2 - 1;
   long upper = (long)(y - g->n / 2 - 1) * (g->n - 1) + x - 1;
   long bottom = (long)(g->n / 2 - 1) * (g->m / 2 - 1) + (g->n - 1) - g->n / 2 - 1; /* position of (n-1, m/2) */
@@ -81,7 +90,7 @@ void cgo_node(const cgo_grid* g, long idx, int* x, int* y) {
     *x = (int)(idx % (g->n - 1)) + 1;
     return;
   }
-  long wB = g->n / 2 - 1, NB = wB * (g->m / 2);
+  long wB = (g->kind == CGO_LSHAPE_ANY) ? g->n - 1 - g->n / 2 : g->n / 2 - 1, NB = wB * (g->m / 2);
   if (idx < NB) {
     *y = (int)(idx / wB) + 1;
     *x = (int)(idx % wB) + g->n / 2 + 1;

@@ -6,8 +6,9 @@
  * Parity pinning: this restatement is checked (tests/test_oracle.py) against
  *   - the reference's golden vectors check.py:4-19, check_debug.py:36, py_debug.txt:5-15, and
  *   - the UNMODIFIED reference sources compiled here into oracle/_ref/libref_cg.so (oracle/Makefile).
- * The RECT (full-rectangle) domain kind has NO reference counterpart: "parity unpinned" for it; it is only
- * checked against an independent scipy sparse solve and the analytic solution.
+ * The RECT (full-rectangle) and LSHAPE_ANY (L-shape for any n, m with the reference's numbering defects repaired)
+ * domain kinds have NO reference counterpart: "parity unpinned" for them; they are only checked against an
+ * independent scipy sparse solve, the analytic solution, and (LSHAPE_ANY at even n == m) the LSHAPE kind itself.
  */
 #ifndef CG_ORACLE_H
 #define CG_ORACLE_H
@@ -16,7 +17,7 @@
 extern "C" {
 #endif
 
-enum { CGO_LSHAPE = 0, CGO_RECT = 1 };
+enum { CGO_LSHAPE = 0, CGO_RECT = 1, CGO_LSHAPE_ANY = 3 };
 
 typedef struct {
   int n, m;           /* numbers of intervals in x and y (grid_system.cpp:314-315) */

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "libcg_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_cg.so")
 
-LSHAPE, RECT = 0, 1
+LSHAPE, RECT, LSHAPE_ANY = 0, 1, 3
 STOP_NAMES = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

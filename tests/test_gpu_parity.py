@@ -339,6 +339,30 @@ def test_rect_solve_vs_oracle(capi, oracle_mod, n):
         assert np.max(np.abs(x - o.true_solution())) < 1e-3  # O(h^2) against the analytic solution
 
 
+@pytest.mark.parametrize("n,m", [(7, 7), (9, 12), (33, 20), (1201, 777), (640, 640)])
+def test_general_lshape_vs_oracle(capi, oracle_mod, n, m):
+    """B200CG_DOMAIN_LSHAPE_ANY: the L-shaped region for odd / non-square grids (parity unpinned: the reference has no
+    valid counterpart); identical to the reference geometry for even n == m."""
+    o = oracle_mod.Oracle(m, n, 0.0, 1.0, 0.0, 1.0, oracle_mod.LSHAPE_ANY)
+    with capi.Plan(m, n, 0.0, 1.0, 0.0, 1.0, domain=capi.DOMAIN_LSHAPE_ANY) as p:
+        assert p.N == o.N
+        v = np.random.default_rng(n).standard_normal(o.N)
+        assert np.array_equal(p.apply(v), o.apply(v))
+        p.build_rhs()
+        assert relmax(p.get_rhs(), o.rhs()) < 1e-14
+        nnz = p.assemble_csr()
+        for a, b in zip(p.get_csr(nnz), o.csr()):
+            assert np.array_equal(a, b)
+        if n <= 64:
+            ref = o.mf_solve(eps=1e-10, max_it=5000)
+            for path in (0, 1):
+                x, info = p.solve(b=o.rhs(), eps_rel=1e-10, max_it=5000, small_grid_path=path)
+                assert abs(info["iterations"] - ref["iterations"]) <= 1 and relmax(x, ref["x"]) < REL
+        if n == m and n % 2 == 0:
+            with capi.Plan(m, n, 0.0, 1.0, 0.0, 1.0, domain=capi.DOMAIN_LSHAPE) as q:
+                assert np.array_equal(q.apply(v), p.apply(v))
+
+
 # ---------------------------------------------------------------- sizes of BASELINE.json
 def test_config2_fixed_iterations_vs_oracle(capi, oracle_mod):
     """4096^2 (12.6 M unknowns): 5 iterations, x / ||r|| against the oracle at the same count.

@@ -177,3 +177,37 @@ def test_dof_counts(oracle_mod):
     for n, N in [(6, 16), (30, 616), (128, 12033)]:
         assert oracle_mod.Oracle(n, n).N == N
     assert oracle_mod.Oracle(128, 128, kind=1).N == 127 * 127
+
+
+# ---------------------------------------------------------------- repaired general L-shape (no reference counterpart)
+def test_lshape_any_equals_reference_geometry_where_the_reference_is_valid(oracle_mod):
+    for n in (6, 30, 64):
+        ref = oracle_mod.Oracle(n, n, 1.0, 2.0, 1.0, 2.0, oracle_mod.LSHAPE)
+        gen = oracle_mod.Oracle(n, n, 1.0, 2.0, 1.0, 2.0, oracle_mod.LSHAPE_ANY)
+        assert ref.N == gen.N and np.array_equal(ref.rhs(), gen.rhs())
+        x = np.random.default_rng(n).standard_normal(ref.N)
+        assert np.array_equal(ref.apply(x), gen.apply(x))
+        for a, b in zip(ref.csr(), gen.csr()):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,m", [(7, 7), (9, 12), (33, 20)])
+def test_lshape_any_is_a_well_formed_system(oracle_mod, n, m):
+    """Odd and non-square grids, where the reference builds a malformed system or crashes: the repaired
+    numbering is a bijection, the operator is symmetric, CG converges to the analytic solution at O(h^2)."""
+    o = oracle_mod.Oracle(m, n, 0.0, 1.0, 0.0, 1.0, oracle_mod.LSHAPE_ANY)
+    seen = set()
+    for y in range(m + 1):
+        for x in range(n + 1):
+            i = o.index(x, y)
+            if i >= 0:
+                assert o.node(i) == (x, y)
+                seen.add(i)
+    assert seen == set(range(o.N))
+    row_map, entries, values = o.csr()
+    assert np.all(np.diff(row_map) <= 5) and entries.min() >= 0 and entries.max() < o.N
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(o.N), rng.standard_normal(o.N)
+    assert abs(np.dot(x, o.apply(y)) - np.dot(y, o.apply(x))) <= 1e-9 * abs(np.dot(x, o.apply(y))) + 1e-9
+    s = o.mf_solve(eps=1e-12, max_it=5000)
+    assert s["converged"] and np.max(np.abs(s["x"] - o.true_solution())) < 5e-3
