@@ -32,11 +32,14 @@ def _sources(directory: str, exts: tuple[str, ...]) -> list[str]:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "b200cg.h")]
     if force or _newer(LIB, deps):
-        cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", LIB,
-               os.path.join(CSRC, "b200cg.cu"), os.path.join(CSRC, "comm.cu"), "-ldl"]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.check_call(cmd)
+        # one nvcc per translation unit, in parallel (the sweep-kernel instantiations dominate the build time)
+        units = ["plan.cu", "solve.cu", "comm.cu"]
+        objs = [os.path.join(CSRC, u[:-3] + ".o") for u in units]
+        flags = [*ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + (["-Xptxas=-v"] if verbose else [])
+        procs = [subprocess.Popen([NVCC, *flags, "-c", os.path.join(CSRC, u), "-o", o]) for u, o in zip(units, objs)]
+        if any(p.wait() != 0 for p in procs):
+            raise RuntimeError("nvcc failed")
+        subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"])
     return LIB
 
 

@@ -48,7 +48,7 @@ __device__ __forceinline__ double slots_max(const double (*slots)[CL_SLOTS], int
   return v;
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) cg_cluster_kernel(const ClusterArgs a) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cg_cluster_kernel(const ClusterArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int nctas = (int)cluster.num_blocks();

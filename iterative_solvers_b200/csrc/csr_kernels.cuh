@@ -133,7 +133,7 @@ __device__ __forceinline__ long long compact_index(const Geom& g, int x, int y) 
   return g.NB + (long long)(y - g.ysplit - 1) * g.wU + (x - 1);
 }
 
-__global__ void csr_count_kernel(int* __restrict__ counts, const Geom g, long long nrows) {
+static __global__ void csr_count_kernel(int* __restrict__ counts, const Geom g, long long nrows) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= nrows;
        i += (long long)gridDim.x * blockDim.x) {
     int c = 0;
@@ -146,7 +146,7 @@ __global__ void csr_count_kernel(int* __restrict__ counts, const Geom g, long lo
   }
 }
 
-__global__ void csr_fill_kernel(const int* __restrict__ row_map, int* __restrict__ entries,
+static __global__ void csr_fill_kernel(const int* __restrict__ row_map, int* __restrict__ entries,
                                 double* __restrict__ values, const Geom g, long long nrows) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows;
        i += (long long)gridDim.x * blockDim.x) {
@@ -193,7 +193,7 @@ static inline int csr_assemble(CsrData* c, const Geom& g, long long nrows, int s
 }
 
 // --------------------------------------------------------------------------------------------- CG kernels
-__global__ void __launch_bounds__(CTA_THREADS) csr_init_kernel(const CsrArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) csr_init_kernel(const CsrArgs a) {
   __shared__ double scratch[3 * 32];
   double s[1] = {0.0}, mx[2] = {0.0, 0.0};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(CTA_THREADS) csr_init_kernel(const CsrArgs a) 
 
 // CG = 0: Az = A z_old (plain SpMV, b200cg_csr_apply).  CG = 1: the fused direction update + SpMV + dots.
 template <int CG>
-__global__ void __launch_bounds__(CTA_THREADS) csr_spmv_kernel(const CsrArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) csr_spmv_kernel(const CsrArgs a) {
   __shared__ double scratch[2 * 32];
   DevState* st = a.st;
   double beta = 0.0;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(CTA_THREADS) csr_spmv_kernel(const CsrArgs a) 
 }
 
 template <int WITH_U>
-__global__ void __launch_bounds__(CTA_THREADS) csr_update_kernel(const CsrArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) csr_update_kernel(const CsrArgs a) {
   __shared__ double scratch[4 * 32];
   DevState* st = a.st;
   if (st->done) return;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(CTA_THREADS) csr_update_kernel(const CsrArgs a
 }
 
 // Az <- A x - b (dirichlet_solver.cpp:147-161)
-__global__ void __launch_bounds__(CTA_THREADS) csr_residual_kernel(const CsrArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) csr_residual_kernel(const CsrArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows;
        i += (long long)gridDim.x * blockDim.x) {
     double sum = 0.0;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(CTA_THREADS) csr_residual_kernel(const CsrArgs
 }
 
 // error = x - u on compact vectors (dirichlet_solver.cpp:172-174); result in Az
-__global__ void __launch_bounds__(CTA_THREADS) csr_error_kernel(const CsrArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) csr_error_kernel(const CsrArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows;
        i += (long long)gridDim.x * blockDim.x)
     a.Az[i] = __dsub_rn(a.x[i], a.u[i]);

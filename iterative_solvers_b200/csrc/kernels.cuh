@@ -56,7 +56,7 @@ struct InitArgs {
   int defer;
 };
 
-__global__ void __launch_bounds__(CTA_THREADS) cg_init_kernel(const InitArgs a) {
+static __global__ void __launch_bounds__(CTA_THREADS) cg_init_kernel(const InitArgs a) {
   __shared__ double scratch[3 * 32];
   double s[1] = {0.0}, mx[2] = {0.0, 0.0};
   const size_t n2 = a.count / 2;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CTA_THREADS) cg_init_kernel(const InitArgs a) 
 
 // After an all-reduce of st->loc_s (sum) and st->loc_m (max) on a sharded plan: every rank forms the same scalars.
 // which: 0 = init, 1 = dot phase, 2 = update phase, 3 = report
-__global__ void finalize_kernel(DevState* st, CbRecord* log, int which, int flags) {
+static __global__ void finalize_kernel(DevState* st, CbRecord* log, int which, int flags) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const bool has_u = (flags & F_U) != 0, report = (flags & F_REPORT) != 0;
   if (which == 0) {
@@ -110,7 +110,7 @@ __global__ void finalize_kernel(DevState* st, CbRecord* log, int which, int flag
 // slots in rank order (identical on every rank) and form the scalars. which: 1 = dot phase, 2 = update phase.
 // One warp: lane r watches rank r. A flag that does not arrive within PEER_TIMEOUT_NS ends the solve with comm_error.
 constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
-__global__ void peer_finalize_kernel(DevState* st, CbRecord* log, const PeerLinks* pl, int which, int flags) {
+static __global__ void peer_finalize_kernel(DevState* st, CbRecord* log, const PeerLinks* pl, int which, int flags) {
   const int lane = threadIdx.x;
   if (st->done) return;
   const int phase = which - 1;
@@ -157,7 +157,7 @@ __global__ void peer_finalize_kernel(DevState* st, CbRecord* log, const PeerLink
 }
 
 // x += alpha_prev * p over the owned rows: settles the update an even (NOX) last iteration left pending.
-__global__ void __launch_bounds__(CTA_THREADS) x_flush_kernel(double* __restrict__ x, const double* __restrict__ p,
+static __global__ void __launch_bounds__(CTA_THREADS) x_flush_kernel(double* __restrict__ x, const double* __restrict__ p,
                                                              DevState* st, size_t begin, size_t count) {
   if (!st->x_pending) return;
   const double alpha = st->alpha_prev;
@@ -194,7 +194,7 @@ __device__ __forceinline__ size_t pitched_off(const Geom& g, int x, int y) {
   return (size_t)(y - g.ybase) * (size_t)g.pitch + (size_t)(x + XOFF);
 }
 
-__global__ void scatter_compact_kernel(const double* __restrict__ compact, double* __restrict__ pitched,
+static __global__ void scatter_compact_kernel(const double* __restrict__ compact, double* __restrict__ pitched,
                                        const Geom g) {
   const long long cnt = g.hi - g.lo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
@@ -204,7 +204,7 @@ __global__ void scatter_compact_kernel(const double* __restrict__ compact, doubl
     pitched[pitched_off(g, x, y)] = compact[i];
   }
 }
-__global__ void gather_compact_kernel(const double* __restrict__ pitched, double* __restrict__ compact,
+static __global__ void gather_compact_kernel(const double* __restrict__ pitched, double* __restrict__ compact,
                                       const Geom g) {
   const long long cnt = g.hi - g.lo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
@@ -215,7 +215,7 @@ __global__ void gather_compact_kernel(const double* __restrict__ pitched, double
   }
 }
 // error = x - u on the compact staging buffer (dirichlet_solver.cpp:172-174)
-__global__ void gather_diff_kernel(const double* __restrict__ pa, const double* __restrict__ pb,
+static __global__ void gather_diff_kernel(const double* __restrict__ pa, const double* __restrict__ pb,
                                    double* __restrict__ compact, const Geom g) {
   const long long cnt = g.hi - g.lo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
@@ -248,7 +248,7 @@ __device__ __forceinline__ bool bottom_bdry(const Geom& g, int x, int y) {
 
 // what: 0 = rhs b (calculate_value, grid_system.cpp:45-67), 1 = true solution u, 2 = x coordinate, 3 = y coordinate.
 // Written to the pitched vector (dst_pitched) and/or the compact staging buffer (dst_compact).
-__global__ void setup_kernel(double* __restrict__ dst_pitched, double* __restrict__ dst_compact, const Geom g,
+static __global__ void setup_kernel(double* __restrict__ dst_pitched, double* __restrict__ dst_compact, const Geom g,
                              int what) {
   const long long cnt = g.hi - g.lo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;

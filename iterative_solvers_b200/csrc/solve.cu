@@ -1,0 +1,523 @@
+// libb200cg, host side 2/2: the operator and solve entry points - CUDA-graph captured CG loop with device-resident
+// scalars, the single-cluster small-grid path, feedback balancing between launches, post-processing.
+#include "sweep_launch.cuh"
+
+using namespace b200cg;
+
+extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_host) {
+  if (!P || !x_host || !y_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host/y_host is NULL");
+  NEED_GEOMETRY(P);
+  CU(cudaSetDevice(P->desc.device));
+  RET(ensure_scratch(P));
+  RET(upload_vector(P, x_host, P->va));
+  RET(exchange_halo(P, P->va));
+  TileArgs a = base_args(P);
+  a.p_in = P->va;
+  a.out = P->vb;
+  RET((launch_tile<MODE_APPLY, 0>(P, a, P->stream)));
+  RET(download_vector(P, P->vb, y_host));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------- solve
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8 };
+
+// Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
+// read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
+static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
+  cudaStream_t s = P->stream;
+  const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR, xdefer = variant & V_XDEFER;
+  int kernels = 0;
+  CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = B200CG_OK;
+  for (int k = 0; k < iters && rc == B200CG_OK; ++k) {
+    const int par = k & 1;
+    if (k == 0) cudaEventRecordWithFlags(P->ev[0], s, cudaEventRecordExternal);
+    if (csr) {
+      // assembled path: p update + SpMV + dots, then the shared update pass
+      csr_spmv_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+          csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+      if (with_u)
+        csr_update_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      else
+        csr_update_kernel<0><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
+            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+      continue;
+    }
+    TileArgs a = base_args(P);
+    a.r_in = P->r[par];
+    a.p_in = P->p[par];
+    a.x = P->x;
+    a.r_out = P->r[par ^ 1];
+    a.p_out = P->p[par ^ 1];
+    a.u = P->u;
+    const int fl = xdefer ? ((k & 1) ? F_X2 : F_NOX) : ((with_u ? F_U : 0) | (report ? F_REPORT : 0));
+    // sharded plans: reductions and halo rows over NVLink peer memory (no NCCL call in the loop); the per-iteration
+    // report variant keeps the NCCL exchange
+    const bool peer = P->desc.world > 1 && P->peer_mode && !report;
+    if (peer) {
+      a.defer = 2;
+      a.peers = P->d_links;
+      const Geom& g = P->g;
+      const int rank = P->desc.rank;
+      if (rank > 0) {  // neighbour below: its top halo row is its last stored row
+        const size_t rows_below = (size_t)(P->ycuts[rank] - P->ycuts[rank - 1]) + 2;
+        a.nb_r_below = P->nb_below_r[par ^ 1] + (rows_below - 1) * g.pitch;
+        a.nb_p_below = P->nb_below_p[par ^ 1] + (rows_below - 1) * g.pitch;
+      }
+      if (rank + 1 < P->desc.world) {  // neighbour above: its bottom halo row is its stored row 0
+        a.nb_r_above = P->nb_above_r[par ^ 1];
+        a.nb_p_above = P->nb_above_p[par ^ 1];
+      }
+    }
+    rc = launch_tile<MODE_DOT, 0>(P, a, s);
+    ++kernels;
+    if (rc == B200CG_OK && peer) {
+      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 1, fl);
+      ++kernels;
+    } else if (rc == B200CG_OK && P->desc.world > 1) {
+      rc = reduce_and_finalize(P, 1, fl, false, s);
+      ++kernels;
+    }
+    if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+    if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
+    if (rc != B200CG_OK) break;
+    if (xdefer) rc = (k & 1) ? launch_tile<MODE_UPD, F_X2>(P, a, s) : launch_tile<MODE_UPD, F_NOX>(P, a, s);
+    else if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
+    else if (report) rc = launch_tile<MODE_UPD, F_REPORT>(P, a, s);
+    else if (with_u) rc = launch_tile<MODE_UPD, F_U>(P, a, s);
+    else rc = launch_tile<MODE_UPD, 0>(P, a, s);
+    ++kernels;
+    if (rc == B200CG_OK && peer) {
+      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 2, fl);
+      ++kernels;
+    } else if (rc == B200CG_OK && P->desc.world > 1) {
+      rc = reduce_and_finalize(P, 2, fl, /*with_max=*/!xdefer, s);
+      ++kernels;
+      if (rc == B200CG_OK) rc = exchange_halo2(P, P->r[par ^ 1], P->p[par ^ 1]);
+    }
+    if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+    if (k == 1 && !report) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
+    if (rc == B200CG_OK && report) {
+      TileArgs ra = base_args(P);
+      ra.p_in = P->x;
+      ra.r_in = P->b;
+      ra.u = P->u;
+      if (P->desc.world > 1) rc = exchange_halo(P, P->x);
+      if (rc == B200CG_OK)
+        rc = with_u ? launch_tile<MODE_APPLY, F_REPORT | F_U>(P, ra, s)
+                    : launch_tile<MODE_APPLY, F_REPORT>(P, ra, s);
+      ++kernels;
+      if (rc == B200CG_OK && P->desc.world > 1) {
+        rc = reduce_and_finalize(P, 3, fl, false, s);
+        ++kernels;
+      }
+    }
+  }
+  cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != B200CG_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(B200CG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(B200CG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  out->exec = exec;
+  out->iters = iters;
+  out->kernels = kernels;
+  return B200CG_OK;
+}
+
+// Small-grid path: how many CTAs a cluster needs to hold r, p, x of the grid in shared memory (0 = does not fit).
+static int cluster_ctas_for(const b200cg_plan_s* P, int* rows_per_cta, size_t* smem) {
+  if (P->generic || P->desc.world > 1) return 0;
+  const Geom& g = P->g;
+  // 8 CTAs (portable cluster size) for the smallest grids, where the per-iteration cost is the three cluster
+  // barriers; 16 CTAs (non-portable size, B200 allows it) once a band would exceed 16 rows: the sweep over the band
+  // is what takes the time there (n = 250: 11.6 us/iteration with 8 CTAs).
+  const int order[2] = {(g.m - 1 > 128 && P->cluster16_ok) ? 16 : 8, (g.m - 1 > 128 && P->cluster16_ok) ? 8 : 16};
+  for (int c : order) {
+    if (c == 16 && !P->cluster16_ok) continue;
+    const int rpc = (g.m - 1 + c - 1) / c;
+    const size_t bytes = cluster_smem_bytes(rpc, g.pitch);
+    if (bytes <= 200 * 1024) {
+      *rows_per_cta = rpc;
+      *smem = bytes;
+      return c;
+    }
+  }
+  return 0;
+}
+
+static int launch_cluster_solve(b200cg_plan_s* P, int ctas, int rows_per_cta, size_t smem, bool with_u, cudaStream_t s) {
+  CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ctas > 8) CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  ClusterArgs ca;
+  ca.b = P->b;
+  ca.u = with_u ? P->u : nullptr;
+  ca.x = P->x;
+  ca.st = P->d_state;
+  ca.cb_log = P->d_log;
+  ca.stop_flag = P->d_stop;
+  ca.g = P->g;
+  ca.rows_per_cta = rows_per_cta;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas, 1, 1);
+  cfg.blockDim = dim3(CL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, cg_cluster_kernel, ca));
+  return B200CG_OK;
+}
+
+static int default_iters_per_graph(const b200cg_plan_s* P) {
+  // small grids are launch-bound: long graphs; big grids: keep the stop/interrupt latency around 0.1 s
+  const long long n = local_count(P);
+  if (n <= (1LL << 20)) return 100;
+  if (n <= (1LL << 24)) return 50;
+  return 20;
+}
+
+extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
+                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
+                            const volatile int* stop_flag) {
+  if (!P || !prm || !info) return fail(B200CG_ERR_INVALID_ARG, "plan/params/info is NULL");
+  if (prm->op != B200CG_OP_MATRIX_FREE && prm->op != B200CG_OP_CSR) return fail(B200CG_ERR_INVALID_ARG, "unknown operator %d", prm->op);
+  if (prm->rule != B200CG_RULE_REL_L2 && prm->rule != B200CG_RULE_MAXNORM) return fail(B200CG_ERR_INVALID_ARG, "unknown rule %d", prm->rule);
+  if (!prm->rhs_on_device && !b_host) return fail(B200CG_ERR_INVALID_ARG, "b_host is NULL and rhs_on_device is 0");
+  if (prm->rhs_on_device && !P->have_rhs) return fail(B200CG_ERR_STATE, "rhs_on_device set but the plan holds no rhs");
+  if (!prm->keep_x_on_device && !x_host) return fail(B200CG_ERR_INVALID_ARG, "x_host is NULL and keep_x_on_device is 0");
+  const bool csr = prm->op == B200CG_OP_CSR;
+  if (!csr) NEED_GEOMETRY(P);
+  if (csr && !P->csr.row_map) return fail(B200CG_ERR_STATE, "CSR solve without a matrix: call b200cg_set_csr / b200cg_assemble_csr");
+  if (csr && prm->rule == B200CG_RULE_REL_L2 && cb) return fail(B200CG_ERR_UNSUPPORTED, "per-iteration report callbacks exist only on the matrix-free path");
+  memset(info, 0, sizeof(*info));
+  const double t_begin = now_ms();
+  CU(cudaSetDevice(P->desc.device));
+  cudaStream_t s = P->stream;
+  const long long cnt = local_count(P);
+  info->local_unknowns = cnt;
+  P->have_solution = false;
+
+  // ---- inputs
+  CU(cudaEventRecord(P->ev[3], s));
+  const bool with_u = (u_host != nullptr);
+  if (csr) {
+    // the assembled path works on compact vectors: host data goes straight into them
+    std::string err;
+    int rc = csr_ensure_vectors(&P->csr, s, &err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if (!prm->rhs_on_device) {
+      CU(cudaMemcpyAsync(P->csr.b, b_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    } else {
+      gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
+      info->kernel_launches += 1;
+    }
+    if (with_u) {
+      CU(cudaMemcpyAsync(P->csr.u, u_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    }
+    P->csr.has_u = with_u;
+  } else {
+    if (!prm->rhs_on_device) {
+      RET(upload_vector(P, b_host, P->b));
+      P->have_rhs = true;
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+      info->kernel_launches += 1;
+    }
+    if (with_u) {
+      RET(ensure_u(P));
+      RET(upload_vector(P, u_host, P->u));
+      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+      info->kernel_launches += 1;
+    }
+  }
+  P->have_u = with_u;
+  CU(cudaEventRecord(P->ev[4], s));
+
+  // ---- device-side solver state
+  const bool report = (prm->rule == B200CG_RULE_REL_L2) && (cb != nullptr);
+  DevState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.eps_rel = prm->eps_rel;
+  hs.eps_p = prm->eps_p;
+  hs.eps_r = prm->eps_r;
+  hs.eps_e = prm->eps_e;
+  hs.max_it = prm->max_it;
+  hs.rule = prm->rule;
+  hs.has_u = with_u ? 1 : 0;
+  hs.callback_every = (cb && prm->rule == B200CG_RULE_MAXNORM) ? (prm->callback_every > 0 ? prm->callback_every : 100) : 0;
+  hs.epoch[0] = P->peer_epoch[0];  // the PeerSync flags are monotonic over the plan's life
+  hs.epoch[1] = P->peer_epoch[1];
+  *P->h_state = hs;
+  CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
+
+  // ---- path: grids that fit one thread-block cluster's shared memory run as a single resident kernel
+  int cl_rows = 0;
+  size_t cl_smem = 0;
+  int cl_ctas = 0;
+  {
+    const long long cb_records = 2 + (long long)std::max(prm->max_it, 0) / 100;
+    const bool eligible = !csr && !report && prm->small_grid_path != 1 && P->cluster_enabled &&
+                          !(cb && cb_records > CB_LOG_CAP);
+    if (eligible) cl_ctas = cluster_ctas_for(P, &cl_rows, &cl_smem);
+    if (prm->small_grid_path == 2 && cl_ctas == 0)
+      return fail(B200CG_ERR_UNSUPPORTED, "small_grid_path = 2 but this solve cannot run in one cluster "
+                                          "(grid too large, sharded plan, CSR operator or per-iteration report)");
+  }
+  const bool use_cluster = cl_ctas > 0;
+
+  bool xdefer = false;
+  unsigned int consumed = 0;
+  bool interrupted = false;
+  double dot_ms = 0.0, upd_even = 0.0, upd_odd = 0.0;
+  int samples = 0, it_before = 0, it_launch0 = 0;
+  (void)it_before;
+  (void)it_launch0;
+  if (use_cluster) {
+    *P->h_stop = 0;
+    CU(cudaEventRecord(P->ev[5], s));
+    RET(launch_cluster_solve(P, cl_ctas, cl_rows, cl_smem, with_u, s));
+    info->kernel_launches += 1;
+    CU(cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(P->ev[8], s));
+    // the kernel polls the mapped flag every CL_POLL_EVERY iterations; forward the caller's stop request
+    for (int spins = 0; cudaEventQuery(P->ev[8]) == cudaErrorNotReady; ++spins) {
+      if (stop_flag && *stop_flag) *P->h_stop = 1;
+      if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));  // long solve: stop burning a core
+    }
+    CU(cudaStreamSynchronize(s));
+    const DevState& st = *P->h_state;
+    interrupted = st.stop_reason == B200CG_STOP_INTERRUPTED;
+    if (cb)
+      for (; consumed < st.n_log; ++consumed) {
+        const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
+        cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
+      }
+  } else {
+    if (csr) {
+      csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      info->kernel_launches += 1;
+    } else {
+      const Geom& g = P->g;
+      InitArgs ia;
+      ia.b = P->b;
+      ia.u = with_u ? P->u : nullptr;
+      ia.r = P->r[0];
+      ia.p = P->p[0];
+      ia.x = P->x;
+      ia.st = P->d_state;
+      ia.partials = P->d_partials;
+      ia.cb_log = P->d_log;
+      ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
+      ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
+      ia.defer = P->desc.world > 1 ? 1 : 0;
+      cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
+      CU(cudaGetLastError());
+      info->kernel_launches += 1;
+      if (P->desc.world > 1) {
+        RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
+        RET(exchange_halo2(P, P->r[0], P->p[0]));
+        info->kernel_launches += 1;
+      }
+    }
+
+    // ---- the captured loop
+    int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
+    if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
+    K = std::max(2, (K + 1) & ~1);
+    K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
+    // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
+    xdefer = P->x_deferral && !csr && !report && prm->rule == B200CG_RULE_REL_L2;
+    const int variant = xdefer ? V_XDEFER : ((with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0));
+    const int key = variant * 4096 + K;
+    GraphEntry& ge = P->graphs[key];
+    if (!ge.exec) RET(build_graph(P, variant, K, &ge));
+
+    CU(cudaEventRecord(P->ev[5], s));
+    // the init kernel's verdict (0 iterations) and record come back with the first graph launch
+    for (;;) {
+      CU(cudaGraphLaunch(ge.exec, s));
+      info->kernel_launches += ge.kernels;
+      CU(cudaStreamSynchronize(s));
+      const DevState& st = *P->h_state;
+      // Event nodes bracket the kernels of the first two captured iterations; count the sample only if those
+      // iterations really ran in this launch (it advanced by at least 2 and the run was not already over).
+      if (!csr && !report && st.it - it_before >= 2) {
+        float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
+        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess &&
+            cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
+          dot_ms += 0.5 * (d0 + d1);
+          upd_even += u0;
+          upd_odd += u1;
+          ++samples;
+        }
+      } else if ((csr || report) && st.it - it_before >= 1) {
+        float d0 = 0.f, u0 = 0.f;
+        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
+          dot_ms += d0;
+          upd_even += u0;
+          upd_odd += u0;
+          ++samples;
+        }
+      }
+      it_before = st.it;
+      if (cb) {
+        for (; consumed < st.n_log; ++consumed) {
+          const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
+          cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
+        }
+      } else {
+        consumed = st.n_log ? st.n_log : 1;
+      }
+      if (consumed == 0) consumed = 1;
+      if (st.done) break;
+      if (P->balance_rounds > 0 && !csr && st.it - it_launch0 >= 2) {
+        // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
+        for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
+        --P->balance_rounds;
+      }
+      it_launch0 = st.it;
+      if (stop_flag && *stop_flag) {
+        interrupted = true;
+        break;
+      }
+    }
+}
+  CU(cudaEventRecord(P->ev[6], s));
+
+  // ---- outputs
+  const DevState st = *P->h_state;
+  P->peer_epoch[0] = st.epoch[0];
+  P->peer_epoch[1] = st.epoch[1];
+  if (st.comm_error) return fail(B200CG_ERR_COMM, "peer-memory exchange timed out after %d iterations (a rank stopped publishing)", st.it);
+  if (xdefer && st.x_pending) {  // the loop ended on an even iteration: settle x += alpha * p
+    const Geom& g = P->g;
+    const size_t begin = (size_t)(g.ylo - g.ybase) * g.pitch, count = (size_t)(g.yhi - g.ylo) * g.pitch;
+    x_flush_kernel<<<ew_grid(P, (long long)(count / 2)), CTA_THREADS, 0, s>>>(P->x, P->p[st.it & 1], P->d_state, begin, count);
+    CU(cudaGetLastError());
+    info->kernel_launches += 1;
+  }
+  P->solution_in_csr = csr;
+  if (!prm->keep_x_on_device) {
+    if (csr) {
+      CU(cudaMemcpyAsync(x_host, P->csr.x, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      RET(download_vector(P, P->x, x_host));
+      info->kernel_launches += 1;
+    }
+    info->d2h_bytes += cnt * (int64_t)sizeof(double);
+  }
+  CU(cudaEventRecord(P->ev[7], s));
+  CU(cudaStreamSynchronize(s));
+  P->have_solution = true;
+
+  info->iterations = st.it;
+  info->converged = interrupted ? 0 : st.converged;
+  info->stop_reason = interrupted ? B200CG_STOP_INTERRUPTED : st.stop_reason;
+  info->r0_l2 = st.r0_norm;
+  info->r_l2 = st.r_norm;
+  info->r_max = st.r_max;
+  info->dx_max = st.dx_max;
+  info->err_max = st.err_max;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, P->ev[3], P->ev[4]);
+  info->h2d_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[5], P->ev[6]);
+  info->solve_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[6], P->ev[7]);
+  info->d2h_ms = ms;
+  cudaEventElapsedTime(&ms, P->ev[3], P->ev[7]);
+  info->device_ms = ms;
+  info->dot_kernel_ms = samples ? dot_ms / samples : 0.0;
+  info->upd_kernel_ms = samples ? 0.5 * (upd_even + upd_odd) / samples : 0.0;
+  info->upd_even_ms = samples ? upd_even / samples : 0.0;
+  info->upd_odd_ms = samples ? upd_odd / samples : 0.0;
+  info->x_deferral = xdefer ? 1 : 0;
+  info->cluster_path = use_cluster ? 1 : 0;
+  info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !report && !use_cluster) ? 1 : 0;
+  info->kernel_samples = samples;
+  // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
+  if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);
+  info->total_ms = now_ms() - t_begin;
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_get_solution(b200cg_plan_t P, double* x_host) {
+  if (!P || !x_host) return fail(B200CG_ERR_INVALID_ARG, "plan/x_host is NULL");
+  if (!P->have_solution) return fail(B200CG_ERR_STATE, "no solution in the plan: call b200cg_solve first");
+  CU(cudaSetDevice(P->desc.device));
+  if (P->solution_in_csr)
+    CU(cudaMemcpyAsync(x_host, P->csr.x, local_count(P) * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  else
+    RET(download_vector(P, P->x, x_host));
+  CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_postprocess(b200cg_plan_t P, int op, double* residual_host, double* error_host) {
+  if (!P) return fail(B200CG_ERR_INVALID_ARG, "plan is NULL");
+  if (!P->have_solution) return fail(B200CG_ERR_STATE, "no solution in the plan: call b200cg_solve first");
+  CU(cudaSetDevice(P->desc.device));
+  cudaStream_t s = P->stream;
+  const long long cnt = local_count(P);
+  if ((op == B200CG_OP_CSR) != P->solution_in_csr)
+    return fail(B200CG_ERR_STATE, "postprocess operator differs from the operator of the last solve");
+  if (residual_host) {
+    if (op == B200CG_OP_CSR) {
+      if (!P->csr.row_map) return fail(B200CG_ERR_STATE, "no CSR matrix in the plan");
+      // A x - b with the assembled matrix (dirichlet_solver.cpp:147-161): z[0] <- x, Az <- A x - b
+      csr_residual_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(residual_host, P->csr.Az, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      RET(ensure_scratch(P));
+      RET(exchange_halo(P, P->x));
+      TileArgs a = base_args(P);
+      a.p_in = P->x;
+      a.r_in = P->b;
+      a.out = P->vb;
+      RET((launch_tile<MODE_APPLY, F_SUB_B>(P, a, s)));
+      RET(download_vector(P, P->vb, residual_host));
+    }
+  }
+  if (error_host) {
+    if (!P->have_u) return fail(B200CG_ERR_STATE, "error = x - u needs the true solution passed to the last solve");
+    if (op == B200CG_OP_CSR) {
+      csr_error_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(error_host, P->csr.Az, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {
+      gather_diff_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->x, P->u, P->compact, P->g);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(error_host, P->compact, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CU(cudaStreamSynchronize(s));
+  return B200CG_OK;
+}
+

@@ -1,0 +1,99 @@
+// Launch side of the sweep kernel: launch shapes, flavour -> tile table, common kernel arguments, and the
+// NCCL-fallback reduce-and-finalize step of sharded plans. Header-only so that every translation unit instantiates
+// just the kernel flavours it launches.
+#pragma once
+#include "plan.h"
+
+namespace b200cg {
+
+// Launch shapes of the sweep kernel. A shape = rows per stage (HS), stages (NST), resident CTAs per SM (CTAS);
+// the bulk-copy destinations take ~96 KB per CTA at 2 CTAs/SM and ~64-72 KB at 3. Shape 0 is the default; the
+// others exist for the hot flavours only and are selected per plan with B200CG_SHAPE_DOT / _UPD / _NOX
+// (tuning knobs).
+template <int NSTREAM, int SHAPE>
+struct ShapeOf;
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 0> {  // HS = 2, 2 CTAs/SM
+  static constexpr int HS = 2, CTAS = 2, NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 6 : (NSTREAM == 3 ? 4 : 3));
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 1> {  // HS = 2, 3 CTAs/SM
+  static constexpr int HS = 2, CTAS = 3, NST = NSTREAM == 1 ? 8 : (NSTREAM == 2 ? 4 : 3);
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 2> {  // HS = 4, 2 CTAs/SM
+  static constexpr int HS = 4, CTAS = 2, NST = NSTREAM == 1 ? 6 : (NSTREAM == 2 ? 3 : 2);
+};
+template <int NSTREAM>
+struct ShapeOf<NSTREAM, 3> {  // HS = 4, 3 CTAs/SM (two-stream flavours only)
+  static constexpr int HS = 4, CTAS = 3, NST = 2;
+};
+
+template <int MODE, int FLAGS, int SHAPE>
+static int launch_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
+  using Sh = ShapeOf<StreamCfg<MODE, FLAGS>::NSTREAM, SHAPE>;
+  auto kernel = cg_stream_kernel<MODE, FLAGS, Sh::HS, Sh::NST, Sh::CTAS>;
+  constexpr size_t smem = stream_smem_bytes<MODE, FLAGS, Sh::HS, Sh::NST>();
+  static thread_local bool configured[64] = {};
+  const int dev = P->desc.device & 63;
+  if (!configured[dev]) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  // flavour: 0 = dot phase, 1 = update without x (NOX), 2 = everything else (its table is cut for 2 CTAs/SM)
+  constexpr int fl = (MODE == MODE_DOT && FLAGS == 0) ? 0 : ((MODE == MODE_UPD && FLAGS == F_NOX) ? 1 : 2);
+  const TileTable& tt = P->tile_tab[fl];
+  if (tt.n_tiles <= 0) return B200CG_OK;
+  a.tiles = tt.d_tiles;
+  a.cta_begin = tt.d_cta_begin;
+  // only the three hot kernels stamp their CTAs (flavour 2 = the x-touching update of the default path)
+  constexpr bool stamped = fl < 2 || (MODE == MODE_UPD && (FLAGS == F_X2 || FLAGS == 0));
+  a.cta_clock = stamped ? P->d_clock[fl] : nullptr;
+  if (stamped) P->clock_ctas[fl] = tt.grid;
+  kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+
+// hot flavours get every shape; the rest run shape 0
+template <int MODE, int FLAGS>
+static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  constexpr bool hot = (MODE == MODE_DOT && FLAGS == 0) ||
+                       (MODE == MODE_UPD && (FLAGS == 0 || FLAGS == F_NOX || FLAGS == F_X2));
+  if constexpr (hot) {
+    constexpr int nstream = StreamCfg<MODE, FLAGS>::NSTREAM;
+    const int shape = MODE == MODE_DOT ? P->shape_dot : (FLAGS == F_NOX ? P->shape_nox : P->shape_upd);
+    switch (shape) {
+      case 1: return launch_shape<MODE, FLAGS, 1>(P, a, s);
+      case 2: return launch_shape<MODE, FLAGS, 2>(P, a, s);
+      case 3:
+        if constexpr (nstream == 2) return launch_shape<MODE, FLAGS, 3>(P, a, s);
+        break;
+      default: break;
+    }
+  }
+  return launch_shape<MODE, FLAGS, 0>(P, a, s);
+}
+
+static TileArgs base_args(b200cg_plan_s* P) {
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.st = P->d_state;
+  a.partials = P->d_partials;
+  a.cb_log = P->d_log;
+  a.defer = P->desc.world > 1 ? 1 : 0;  // build_graph switches the loop kernels to 2 (peer memory) when it can
+  a.g = P->g;
+  return a;
+}
+
+// sharded plans: all-reduce this rank's totals, then every rank forms the same scalars (finalize_kernel)
+static int reduce_and_finalize(b200cg_plan_s* P, int which, int flags, bool with_max, cudaStream_t s) {
+  if (P->desc.world <= 1) return B200CG_OK;
+  std::string err;
+  if (!comm_allreduce_state(&P->comm, P->d_state, with_max, s, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+  finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, which, flags);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+
+}  // namespace b200cg
