@@ -196,9 +196,24 @@ static int default_iters_per_graph(const b200cg_plan_s* P) {
   return 20;
 }
 
-extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
-                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
-                            const volatile int* stop_flag) {
+// Everything one b200cg_solve call carries between its phases.
+struct SolveCall {
+  b200cg_plan_s* P;
+  const b200cg_params* prm;
+  b200cg_info* info;
+  b200cg_iter_cb cb;
+  void* user;
+  const volatile int* stop_flag;
+  bool csr, with_u, report;
+  bool xdefer = false, use_cluster = false, interrupted = false;
+  unsigned int consumed = 0;  // callback records already delivered
+  double dot_ms = 0.0, upd_even_ms = 0.0, upd_odd_ms = 0.0;
+  int samples = 0;
+  long long count;  // unknowns of this rank
+};
+
+static int check_solve_args(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, double* x_host,
+                            b200cg_info* info, b200cg_iter_cb cb) {
   if (!P || !prm || !info) return fail(B200CG_ERR_INVALID_ARG, "plan/params/info is NULL");
   if (prm->op != B200CG_OP_MATRIX_FREE && prm->op != B200CG_OP_CSR) return fail(B200CG_ERR_INVALID_ARG, "unknown operator %d", prm->op);
   if (prm->rule != B200CG_RULE_REL_L2 && prm->rule != B200CG_RULE_MAXNORM) return fail(B200CG_ERR_INVALID_ARG, "unknown rule %d", prm->rule);
@@ -209,53 +224,52 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   if (!csr) NEED_GEOMETRY(P);
   if (csr && !P->csr.row_map) return fail(B200CG_ERR_STATE, "CSR solve without a matrix: call b200cg_set_csr / b200cg_assemble_csr");
   if (csr && prm->rule == B200CG_RULE_REL_L2 && cb) return fail(B200CG_ERR_UNSUPPORTED, "per-iteration report callbacks exist only on the matrix-free path");
-  memset(info, 0, sizeof(*info));
-  const double t_begin = now_ms();
-  CU(cudaSetDevice(P->desc.device));
-  cudaStream_t s = P->stream;
-  const long long cnt = local_count(P);
-  info->local_unknowns = cnt;
-  P->have_solution = false;
+  return B200CG_OK;
+}
 
-  // ---- inputs
-  CU(cudaEventRecord(P->ev[3], s));
-  const bool with_u = (u_host != nullptr);
-  if (csr) {
-    // the assembled path works on compact vectors: host data goes straight into them
+// Host vectors -> device (the assembled path keeps compact vectors, the matrix-free path pitched ones).
+static int upload_inputs(SolveCall& c, const double* b_host, const double* u_host) {
+  b200cg_plan_s* P = c.P;
+  cudaStream_t s = P->stream;
+  const int64_t bytes = c.count * (int64_t)sizeof(double);
+  if (c.csr) {
     std::string err;
     int rc = csr_ensure_vectors(&P->csr, s, &err);
     if (rc) return fail(rc, "%s", err.c_str());
-    if (!prm->rhs_on_device) {
-      CU(cudaMemcpyAsync(P->csr.b, b_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
-      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    if (!c.prm->rhs_on_device) {
+      CU(cudaMemcpyAsync(P->csr.b, b_host, bytes, cudaMemcpyHostToDevice, s));
+      c.info->h2d_bytes += bytes;
     } else {
-      gather_compact_kernel<<<ew_grid(P, cnt), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
-      info->kernel_launches += 1;
+      gather_compact_kernel<<<ew_grid(P, c.count), CTA_THREADS, 0, s>>>(P->b, P->csr.b, P->g);
+      c.info->kernel_launches += 1;
     }
-    if (with_u) {
-      CU(cudaMemcpyAsync(P->csr.u, u_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
-      info->h2d_bytes += cnt * (int64_t)sizeof(double);
+    if (c.with_u) {
+      CU(cudaMemcpyAsync(P->csr.u, u_host, bytes, cudaMemcpyHostToDevice, s));
+      c.info->h2d_bytes += bytes;
     }
-    P->csr.has_u = with_u;
+    P->csr.has_u = c.with_u;
   } else {
-    if (!prm->rhs_on_device) {
+    if (!c.prm->rhs_on_device) {
       RET(upload_vector(P, b_host, P->b));
       P->have_rhs = true;
-      info->h2d_bytes += cnt * (int64_t)sizeof(double);
-      info->kernel_launches += 1;
+      c.info->h2d_bytes += bytes;
+      c.info->kernel_launches += 1;
     }
-    if (with_u) {
+    if (c.with_u) {
       RET(ensure_u(P));
       RET(upload_vector(P, u_host, P->u));
-      info->h2d_bytes += cnt * (int64_t)sizeof(double);
-      info->kernel_launches += 1;
+      c.info->h2d_bytes += bytes;
+      c.info->kernel_launches += 1;
     }
   }
-  P->have_u = with_u;
-  CU(cudaEventRecord(P->ev[4], s));
+  P->have_u = c.with_u;
+  return B200CG_OK;
+}
 
-  // ---- device-side solver state
-  const bool report = (prm->rule == B200CG_RULE_REL_L2) && (cb != nullptr);
+// Solver parameters into the device-side state; everything else in it is armed by the init kernel.
+static int arm_device_state(SolveCall& c) {
+  b200cg_plan_s* P = c.P;
+  const b200cg_params* prm = c.prm;
   DevState hs;
   memset(&hs, 0, sizeof(hs));
   hs.eps_rel = prm->eps_rel;
@@ -264,203 +278,246 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   hs.eps_e = prm->eps_e;
   hs.max_it = prm->max_it;
   hs.rule = prm->rule;
-  hs.has_u = with_u ? 1 : 0;
-  hs.callback_every = (cb && prm->rule == B200CG_RULE_MAXNORM) ? (prm->callback_every > 0 ? prm->callback_every : 100) : 0;
+  hs.has_u = c.with_u ? 1 : 0;
+  hs.callback_every = (c.cb && prm->rule == B200CG_RULE_MAXNORM) ? (prm->callback_every > 0 ? prm->callback_every : 100) : 0;
   hs.epoch[0] = P->peer_epoch[0];  // the PeerSync flags are monotonic over the plan's life
   hs.epoch[1] = P->peer_epoch[1];
   *P->h_state = hs;
-  CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(P->d_state, P->h_state, sizeof(DevState), cudaMemcpyHostToDevice, P->stream));
+  return B200CG_OK;
+}
 
-  // ---- path: grids that fit one thread-block cluster's shared memory run as a single resident kernel
-  int cl_rows = 0;
-  size_t cl_smem = 0;
-  int cl_ctas = 0;
-  {
-    const long long cb_records = 2 + (long long)std::max(prm->max_it, 0) / 100;
-    const bool eligible = !csr && !report && prm->small_grid_path != 1 && P->cluster_enabled &&
-                          !(cb && cb_records > CB_LOG_CAP);
-    if (eligible) cl_ctas = cluster_ctas_for(P, &cl_rows, &cl_smem);
-    if (prm->small_grid_path == 2 && cl_ctas == 0)
-      return fail(B200CG_ERR_UNSUPPORTED, "small_grid_path = 2 but this solve cannot run in one cluster "
-                                          "(grid too large, sharded plan, CSR operator or per-iteration report)");
-  }
-  const bool use_cluster = cl_ctas > 0;
-
-  bool xdefer = false;
-  unsigned int consumed = 0;
-  bool interrupted = false;
-  double dot_ms = 0.0, upd_even = 0.0, upd_odd = 0.0;
-  int samples = 0, it_before = 0, it_launch0 = 0;
-  (void)it_before;
-  (void)it_launch0;
-  if (use_cluster) {
-    *P->h_stop = 0;
-    CU(cudaEventRecord(P->ev[5], s));
-    RET(launch_cluster_solve(P, cl_ctas, cl_rows, cl_smem, with_u, s));
-    info->kernel_launches += 1;
-    CU(cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(P->ev[8], s));
-    // the kernel polls the mapped flag every CL_POLL_EVERY iterations; forward the caller's stop request
-    for (int spins = 0; cudaEventQuery(P->ev[8]) == cudaErrorNotReady; ++spins) {
-      if (stop_flag && *stop_flag) *P->h_stop = 1;
-      if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));  // long solve: stop burning a core
+static void deliver_callbacks(SolveCall& c) {
+  const DevState& st = *c.P->h_state;
+  if (c.cb) {
+    for (; c.consumed < st.n_log; ++c.consumed) {
+      const CbRecord& rec = c.P->h_log[c.consumed % CB_LOG_CAP];
+      c.cb(c.user, (int)rec.it, rec.precision, rec.residual, rec.error);
     }
+  } else {
+    c.consumed = st.n_log;
+  }
+}
+
+// Small-grid path: the whole solve is one launch of one thread-block cluster (cluster_kernel.cuh).
+static int run_cluster_solve(SolveCall& c, int ctas, int rows_per_cta, size_t smem) {
+  b200cg_plan_s* P = c.P;
+  cudaStream_t s = P->stream;
+  *P->h_stop = 0;
+  CU(cudaEventRecord(P->ev[5], s));
+  RET(launch_cluster_solve(P, ctas, rows_per_cta, smem, c.with_u, s));
+  c.info->kernel_launches += 1;
+  CU(cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(P->ev[8], s));
+  // the kernel polls the mapped flag every CL_POLL_EVERY iterations; forward the caller's stop request
+  for (int spins = 0; cudaEventQuery(P->ev[8]) == cudaErrorNotReady; ++spins) {
+    if (c.stop_flag && *c.stop_flag) *P->h_stop = 1;
+    if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));  // long solve: stop burning a core
+  }
+  CU(cudaStreamSynchronize(s));
+  c.interrupted = P->h_state->stop_reason == B200CG_STOP_INTERRUPTED;
+  deliver_callbacks(c);
+  return B200CG_OK;
+}
+
+static int launch_init(SolveCall& c) {
+  b200cg_plan_s* P = c.P;
+  cudaStream_t s = P->stream;
+  if (c.csr) {
+    csr_init_kernel<<<csr_grid(c.count, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
+    CU(cudaGetLastError());
+    c.info->kernel_launches += 1;
+    return B200CG_OK;
+  }
+  const Geom& g = P->g;
+  InitArgs ia;
+  ia.b = P->b;
+  ia.u = c.with_u ? P->u : nullptr;
+  ia.r = P->r[0];
+  ia.p = P->p[0];
+  ia.x = P->x;
+  ia.st = P->d_state;
+  ia.partials = P->d_partials;
+  ia.cb_log = P->d_log;
+  ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
+  ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
+  ia.defer = P->desc.world > 1 ? 1 : 0;
+  cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
+  CU(cudaGetLastError());
+  c.info->kernel_launches += 1;
+  if (P->desc.world > 1) {  // once per solve: NCCL
+    RET(reduce_and_finalize(P, 0, c.with_u ? F_U : 0, true, s));
+    RET(exchange_halo2(P, P->r[0], P->p[0]));
+    c.info->kernel_launches += 1;
+  }
+  return B200CG_OK;
+}
+
+// Event nodes bracket the kernels of the first two captured iterations of a graph launch; a sample counts only if
+// those iterations really ran in this launch (`advanced` = iterations completed by it).
+static void sample_kernel_times(SolveCall& c, int advanced) {
+  b200cg_plan_s* P = c.P;
+  float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
+  if (!c.csr && !c.report && advanced >= 2) {
+    if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess && cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess && cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
+      c.dot_ms += 0.5 * (d0 + d1);
+      c.upd_even_ms += u0;
+      c.upd_odd_ms += u1;
+      ++c.samples;
+    }
+  } else if ((c.csr || c.report) && advanced >= 1) {
+    if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess && cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
+      c.dot_ms += d0;
+      c.upd_even_ms += u0;
+      c.upd_odd_ms += u0;
+      ++c.samples;
+    }
+  }
+}
+
+// The general path: init kernel, then graph launches of K captured iterations until the device says done.
+static int run_graph_solve(SolveCall& c) {
+  b200cg_plan_s* P = c.P;
+  const b200cg_params* prm = c.prm;
+  cudaStream_t s = P->stream;
+  RET(launch_init(c));
+  int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
+  if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
+  K = std::max(2, (K + 1) & ~1);
+  K = std::min(K, c.report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
+  // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
+  c.xdefer = P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2;
+  const int variant = c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0));
+  GraphEntry& ge = P->graphs[variant * 4096 + K];
+  if (!ge.exec) RET(build_graph(P, variant, K, &ge));
+
+  CU(cudaEventRecord(P->ev[5], s));
+  int it_before = 0;
+  // the init kernel's verdict (0 iterations) and its callback record come back with the first graph launch
+  for (;;) {
+    CU(cudaGraphLaunch(ge.exec, s));
+    c.info->kernel_launches += ge.kernels;
     CU(cudaStreamSynchronize(s));
     const DevState& st = *P->h_state;
-    interrupted = st.stop_reason == B200CG_STOP_INTERRUPTED;
-    if (cb)
-      for (; consumed < st.n_log; ++consumed) {
-        const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
-        cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
-      }
-  } else {
-    if (csr) {
-      csr_init_kernel<<<csr_grid(cnt, P->sms), CTA_THREADS, 0, s>>>(csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, 0));
-      CU(cudaGetLastError());
-      info->kernel_launches += 1;
-    } else {
-      const Geom& g = P->g;
-      InitArgs ia;
-      ia.b = P->b;
-      ia.u = with_u ? P->u : nullptr;
-      ia.r = P->r[0];
-      ia.p = P->p[0];
-      ia.x = P->x;
-      ia.st = P->d_state;
-      ia.partials = P->d_partials;
-      ia.cb_log = P->d_log;
-      ia.begin = (size_t)(g.ylo - g.ybase) * g.pitch;
-      ia.count = (size_t)(g.yhi - g.ylo) * g.pitch;
-      ia.defer = P->desc.world > 1 ? 1 : 0;
-      cg_init_kernel<<<ew_grid(P, (long long)(ia.count / 2)), CTA_THREADS, 0, s>>>(ia);
-      CU(cudaGetLastError());
-      info->kernel_launches += 1;
-      if (P->desc.world > 1) {
-        RET(reduce_and_finalize(P, 0, with_u ? F_U : 0, true, s));
-        RET(exchange_halo2(P, P->r[0], P->p[0]));
-        info->kernel_launches += 1;
-      }
+    const int advanced = st.it - it_before;
+    it_before = st.it;
+    sample_kernel_times(c, advanced);
+    deliver_callbacks(c);
+    if (st.done) break;
+    if (P->balance_rounds > 0 && !c.csr && advanced >= 2) {
+      // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
+      for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
+      --P->balance_rounds;
     }
-
-    // ---- the captured loop
-    int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
-    if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
-    K = std::max(2, (K + 1) & ~1);
-    K = std::min(K, report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
-    // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
-    xdefer = P->x_deferral && !csr && !report && prm->rule == B200CG_RULE_REL_L2;
-    const int variant = xdefer ? V_XDEFER : ((with_u ? V_U : 0) | (report ? V_REPORT : 0) | (csr ? V_CSR : 0));
-    const int key = variant * 4096 + K;
-    GraphEntry& ge = P->graphs[key];
-    if (!ge.exec) RET(build_graph(P, variant, K, &ge));
-
-    CU(cudaEventRecord(P->ev[5], s));
-    // the init kernel's verdict (0 iterations) and record come back with the first graph launch
-    for (;;) {
-      CU(cudaGraphLaunch(ge.exec, s));
-      info->kernel_launches += ge.kernels;
-      CU(cudaStreamSynchronize(s));
-      const DevState& st = *P->h_state;
-      // Event nodes bracket the kernels of the first two captured iterations; count the sample only if those
-      // iterations really ran in this launch (it advanced by at least 2 and the run was not already over).
-      if (!csr && !report && st.it - it_before >= 2) {
-        float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
-        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
-            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess &&
-            cudaEventElapsedTime(&d1, P->ev[2], P->ev[8]) == cudaSuccess &&
-            cudaEventElapsedTime(&u1, P->ev[8], P->ev[9]) == cudaSuccess) {
-          dot_ms += 0.5 * (d0 + d1);
-          upd_even += u0;
-          upd_odd += u1;
-          ++samples;
-        }
-      } else if ((csr || report) && st.it - it_before >= 1) {
-        float d0 = 0.f, u0 = 0.f;
-        if (cudaEventElapsedTime(&d0, P->ev[0], P->ev[1]) == cudaSuccess &&
-            cudaEventElapsedTime(&u0, P->ev[1], P->ev[2]) == cudaSuccess) {
-          dot_ms += d0;
-          upd_even += u0;
-          upd_odd += u0;
-          ++samples;
-        }
-      }
-      it_before = st.it;
-      if (cb) {
-        for (; consumed < st.n_log; ++consumed) {
-          const CbRecord& rec = P->h_log[consumed % CB_LOG_CAP];
-          cb(user, (int)rec.it, rec.precision, rec.residual, rec.error);
-        }
-      } else {
-        consumed = st.n_log ? st.n_log : 1;
-      }
-      if (consumed == 0) consumed = 1;
-      if (st.done) break;
-      if (P->balance_rounds > 0 && !csr && st.it - it_launch0 >= 2) {
-        // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
-        for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
-        --P->balance_rounds;
-      }
-      it_launch0 = st.it;
-      if (stop_flag && *stop_flag) {
-        interrupted = true;
-        break;
-      }
+    if (c.stop_flag && *c.stop_flag) {
+      c.interrupted = true;
+      break;
     }
+  }
+  return B200CG_OK;
 }
-  CU(cudaEventRecord(P->ev[6], s));
 
-  // ---- outputs
-  const DevState st = *P->h_state;
-  P->peer_epoch[0] = st.epoch[0];
-  P->peer_epoch[1] = st.epoch[1];
-  if (st.comm_error) return fail(B200CG_ERR_COMM, "peer-memory exchange timed out after %d iterations (a rank stopped publishing)", st.it);
-  if (xdefer && st.x_pending) {  // the loop ended on an even iteration: settle x += alpha * p
+// x of the last iterate to the host (settling a pending x-deferral update first).
+static int collect_solution(SolveCall& c, const DevState& st, double* x_host) {
+  b200cg_plan_s* P = c.P;
+  cudaStream_t s = P->stream;
+  if (c.xdefer && st.x_pending) {  // the loop ended on an even iteration: x += alpha * p is still owed
     const Geom& g = P->g;
     const size_t begin = (size_t)(g.ylo - g.ybase) * g.pitch, count = (size_t)(g.yhi - g.ylo) * g.pitch;
     x_flush_kernel<<<ew_grid(P, (long long)(count / 2)), CTA_THREADS, 0, s>>>(P->x, P->p[st.it & 1], P->d_state, begin, count);
     CU(cudaGetLastError());
-    info->kernel_launches += 1;
+    c.info->kernel_launches += 1;
   }
-  P->solution_in_csr = csr;
-  if (!prm->keep_x_on_device) {
-    if (csr) {
-      CU(cudaMemcpyAsync(x_host, P->csr.x, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+  P->solution_in_csr = c.csr;
+  if (!c.prm->keep_x_on_device) {
+    if (c.csr) {
+      CU(cudaMemcpyAsync(x_host, P->csr.x, c.count * sizeof(double), cudaMemcpyDeviceToHost, s));
     } else {
       RET(download_vector(P, P->x, x_host));
-      info->kernel_launches += 1;
+      c.info->kernel_launches += 1;
     }
-    info->d2h_bytes += cnt * (int64_t)sizeof(double);
+    c.info->d2h_bytes += c.count * (int64_t)sizeof(double);
   }
-  CU(cudaEventRecord(P->ev[7], s));
-  CU(cudaStreamSynchronize(s));
-  P->have_solution = true;
+  return B200CG_OK;
+}
 
+static void fill_info(const SolveCall& c, const DevState& st) {
+  b200cg_plan_s* P = c.P;
+  b200cg_info* info = c.info;
   info->iterations = st.it;
-  info->converged = interrupted ? 0 : st.converged;
-  info->stop_reason = interrupted ? B200CG_STOP_INTERRUPTED : st.stop_reason;
+  info->converged = c.interrupted ? 0 : st.converged;
+  info->stop_reason = c.interrupted ? B200CG_STOP_INTERRUPTED : st.stop_reason;
   info->r0_l2 = st.r0_norm;
   info->r_l2 = st.r_norm;
   info->r_max = st.r_max;
   info->dx_max = st.dx_max;
   info->err_max = st.err_max;
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, P->ev[3], P->ev[4]);
-  info->h2d_ms = ms;
-  cudaEventElapsedTime(&ms, P->ev[5], P->ev[6]);
-  info->solve_ms = ms;
-  cudaEventElapsedTime(&ms, P->ev[6], P->ev[7]);
-  info->d2h_ms = ms;
-  cudaEventElapsedTime(&ms, P->ev[3], P->ev[7]);
-  info->device_ms = ms;
-  info->dot_kernel_ms = samples ? dot_ms / samples : 0.0;
-  info->upd_kernel_ms = samples ? 0.5 * (upd_even + upd_odd) / samples : 0.0;
-  info->upd_even_ms = samples ? upd_even / samples : 0.0;
-  info->upd_odd_ms = samples ? upd_odd / samples : 0.0;
-  info->x_deferral = xdefer ? 1 : 0;
-  info->cluster_path = use_cluster ? 1 : 0;
-  info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !report && !use_cluster) ? 1 : 0;
-  info->kernel_samples = samples;
+  auto span = [&](int a, int b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, P->ev[a], P->ev[b]);
+    return (double)ms;
+  };
+  info->h2d_ms = span(3, 4);
+  info->solve_ms = span(5, 6);
+  info->d2h_ms = span(6, 7);
+  info->device_ms = span(3, 7);
+  info->dot_kernel_ms = c.samples ? c.dot_ms / c.samples : 0.0;
+  info->upd_kernel_ms = c.samples ? 0.5 * (c.upd_even_ms + c.upd_odd_ms) / c.samples : 0.0;
+  info->upd_even_ms = c.samples ? c.upd_even_ms / c.samples : 0.0;
+  info->upd_odd_ms = c.samples ? c.upd_odd_ms / c.samples : 0.0;
+  info->kernel_samples = c.samples;
+  info->x_deferral = c.xdefer ? 1 : 0;
+  info->cluster_path = c.use_cluster ? 1 : 0;
+  info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !c.report && !c.use_cluster) ? 1 : 0;
+}
+
+extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
+                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
+                            const volatile int* stop_flag) {
+  RET(check_solve_args(P, prm, b_host, x_host, info, cb));
+  memset(info, 0, sizeof(*info));
+  const double t_begin = now_ms();
+  CU(cudaSetDevice(P->desc.device));
+  cudaStream_t s = P->stream;
+  SolveCall c{P, prm, info, cb, user, stop_flag,
+              /*csr=*/prm->op == B200CG_OP_CSR, /*with_u=*/u_host != nullptr,
+              /*report=*/prm->rule == B200CG_RULE_REL_L2 && cb != nullptr};
+  c.count = local_count(P);
+  info->local_unknowns = c.count;
+  P->have_solution = false;
+
+  CU(cudaEventRecord(P->ev[3], s));
+  RET(upload_inputs(c, b_host, u_host));
+  CU(cudaEventRecord(P->ev[4], s));
+  RET(arm_device_state(c));
+
+  // grids that fit one thread-block cluster's shared memory run as a single resident kernel
+  int cl_rows = 0, cl_ctas = 0;
+  size_t cl_smem = 0;
+  {
+    const long long cb_records = 2 + (long long)std::max(prm->max_it, 0) / 100;
+    const bool eligible = !c.csr && !c.report && prm->small_grid_path != 1 && P->cluster_enabled && !(cb && cb_records > CB_LOG_CAP);
+    if (eligible) cl_ctas = cluster_ctas_for(P, &cl_rows, &cl_smem);
+    if (prm->small_grid_path == 2 && cl_ctas == 0)
+      return fail(B200CG_ERR_UNSUPPORTED, "small_grid_path = 2 but this solve cannot run in one cluster "
+                                          "(grid too large, sharded plan, CSR operator or per-iteration report)");
+  }
+  c.use_cluster = cl_ctas > 0;
+  if (c.use_cluster) RET(run_cluster_solve(c, cl_ctas, cl_rows, cl_smem));
+  else RET(run_graph_solve(c));
+  CU(cudaEventRecord(P->ev[6], s));
+
+  const DevState st = *P->h_state;
+  P->peer_epoch[0] = st.epoch[0];
+  P->peer_epoch[1] = st.epoch[1];
+  if (st.comm_error) return fail(B200CG_ERR_COMM, "peer-memory exchange timed out after %d iterations (a rank stopped publishing)", st.it);
+  RET(collect_solution(c, st, x_host));
+  CU(cudaEventRecord(P->ev[7], s));
+  CU(cudaStreamSynchronize(s));
+  P->have_solution = true;
+  fill_info(c, st);
   // MSGSolver fires one more callback after the loop with the final values (msg_solver.cpp:193-195)
   if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);
   info->total_ms = now_ms() - t_begin;
