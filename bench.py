@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=16384, help="grid intervals per side at 1 GPU")
+    ap.add_argument("--n", "--grid-n", dest="n", type=int, default=16384, help="grid intervals per side at 1 GPU")
     ap.add_argument("--iters", type=int, default=500, help="CG iterations per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): unknowns per GPU fixed; strong: the --n grid sharded over all GPUs "
+                         "(BASELINE.json configs[2])")
     ap.add_argument("--domain", default="lshape", choices=["lshape", "rect"])
     ap.add_argument("--op", default="mf", choices=["mf", "csr"])
     ap.add_argument("--tile-rows", type=int, default=0)
@@ -231,7 +234,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    n = grid_side(args.n, world, args.domain)
+    n = grid_side(args.n, world if args.scaling == "weak" else 1, args.domain)
     domain = capi.DOMAIN_LSHAPE if args.domain == "lshape" else capi.DOMAIN_RECT
     op = capi.OP_MATRIX_FREE if args.op == "mf" else capi.OP_CSR
     plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local_rank, rank=rank, world=world,
@@ -338,7 +341,7 @@ def run_b200(args):
                                    f"{its} iterations, 1 core (the reference code is serial)")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, args.iters, args.domain, args.op), "grid_n": n, "unknowns": plan.N,
                    "unknowns_per_gpu": plan.N / world, "iterations_per_step": args.iters,

@@ -160,6 +160,14 @@ int b200cg_local_range(b200cg_plan_t plan, int64_t* lo, int64_t* hi);
  * [y_lo, y_hi) and compact index range [lo, hi) of desc->rank among desc->world ranks, balanced by unknowns. */
 int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_hi, int64_t* lo, int64_t* hi,
                      int64_t* n_unknowns);
+/* The tile table the sweep kernels of such a plan would walk on a GPU with `sms` SMs and `ctas_per_sm` resident
+ * CTAs per SM (pure host logic, needs no device; for tests and tools). A tile is four ints {col0, ya, yb, xlo}: the
+ * 512-column strip starting at storage column col0, emit rows [ya, yb), first unknown x of these rows; it writes the
+ * unknowns x in [max(col0, xlo), min(col0 + 503, n - 1)]. CTA c walks tiles [cta_begin[c], cta_begin[c + 1]).
+ * weights (n_weights entries, or NULL for the initial equal split) are the per-CTA shares feedback balancing
+ * converges to. tiles holds `capacity` quadruples, cta_begin sms * ctas_per_sm + 1 ints. */
+int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas_per_sm, const double* weights, int n_weights,
+                      int* tiles, int64_t capacity, int64_t* n_tiles, int* cta_begin, int* grid);
 
 /* ------------------------------------------------------------------ setup data (kernel K0)
  * rhs b = f - Dirichlet neighbour terms: calculate_value (grid_system.cpp:45-67),

@@ -19,7 +19,7 @@ ERR_NO_DEVICE = 2
 EXPORTS = [
     "b200cg_last_error", "b200cg_version", "b200cg_device_count", "b200cg_alloc_pinned", "b200cg_free_pinned",
     "b200cg_comm_unique_id", "b200cg_plan_create", "b200cg_plan_destroy", "b200cg_size", "b200cg_local_range",
-    "b200cg_partition",
+    "b200cg_partition", "b200cg_work_split",
     "b200cg_build_rhs", "b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_coords",
     "b200cg_apply", "b200cg_set_csr", "b200cg_assemble_csr", "b200cg_get_csr", "b200cg_csr_apply",
     "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times",
@@ -86,6 +86,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         for name in ("b200cg_get_coords", "b200cg_apply", "b200cg_csr_apply"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200cg_work_split.argtypes = [C.POINTER(PlanDesc), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int)]
         L.b200cg_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.b200cg_local_range.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.b200cg_set_csr.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -125,6 +127,23 @@ def partition(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1):
     ylo, yhi, lo, hi, N = C.c_int(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
     check(lib().b200cg_partition(C.byref(desc), C.byref(ylo), C.byref(yhi), C.byref(lo), C.byref(hi), C.byref(N)))
     return ylo.value, yhi.value, lo.value, hi.value, N.value
+
+
+def work_split(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1, sms=148, ctas_per_sm=2, weights=None, tile_rows=0):
+    """The sweep kernels' tile table for such a plan: (tiles[k, 4] = col0, ya, yb, xlo; cta_begin[grid + 1]).
+    Pure host logic (b200cg_work_split) - works without a GPU."""
+    desc = PlanDesc(n=int(n), m=int(m), a=0.0, b=1.0, c=0.0, d=1.0, domain=int(domain), device=0, rank=int(rank),
+                    world=int(world), tile_rows=int(tile_rows))
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    nw = 0 if w is None else int(w.size)
+    count, grid = C.c_int64(), C.c_int()
+    check(lib().b200cg_work_split(C.byref(desc), int(sms), int(ctas_per_sm), _ptr(w), nw, None, C.c_int64(0),
+                                  C.byref(count), None, C.byref(grid)))
+    tiles = np.zeros((max(count.value, 1), 4), dtype=np.int32)
+    cta_begin = np.zeros(int(sms) * int(ctas_per_sm) + 1, dtype=np.int32)
+    check(lib().b200cg_work_split(C.byref(desc), int(sms), int(ctas_per_sm), _ptr(w), nw, _ptr(tiles),
+                                  C.c_int64(tiles.shape[0]), C.byref(count), _ptr(cta_begin), C.byref(grid)))
+    return tiles[:count.value], cta_begin[:grid.value + 1]
 
 
 def _ptr(a):

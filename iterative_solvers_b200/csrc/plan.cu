@@ -525,6 +525,37 @@ extern "C" int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_
   return B200CG_OK;
 }
 
+extern "C" int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas_per_sm, const double* weights,
+                                 int n_weights, int* tiles_out, int64_t capacity, int64_t* n_tiles, int* cta_begin_out,
+                                 int* grid_out) {
+  if (!desc || !n_tiles || !grid_out) return fail(B200CG_ERR_INVALID_ARG, "desc/n_tiles/grid is NULL");
+  if (sms < 1 || ctas_per_sm < 1) return fail(B200CG_ERR_INVALID_ARG, "sms and ctas_per_sm must be positive");
+  if (desc->domain == B200CG_DOMAIN_GENERIC) return fail(B200CG_ERR_UNSUPPORTED, "a generic (CSR-only) plan has no sweep tiles");
+  b200cg_plan_s tmp;
+  tmp.desc = *desc;
+  RET(setup_geometry(&tmp));
+  tmp.sms = sms;
+  TileTable tt;
+  tt.ctas_per_sm = ctas_per_sm;
+  if (weights && n_weights > 0) tt.weight.assign(weights, weights + n_weights);
+  std::vector<Tile> tiles;
+  std::vector<int> cta_begin;
+  build_tiles(&tmp, &tt, &tiles, &cta_begin);
+  *n_tiles = (int64_t)tiles.size();
+  *grid_out = tt.grid;
+  if (tiles_out) {
+    if ((int64_t)tiles.size() > capacity) return fail(B200CG_ERR_INVALID_ARG, "%zu tiles do not fit capacity %lld", tiles.size(), (long long)capacity);
+    for (size_t i = 0; i < tiles.size(); ++i) {
+      tiles_out[4 * i + 0] = tiles[i].col0;
+      tiles_out[4 * i + 1] = tiles[i].ya;
+      tiles_out[4 * i + 2] = tiles[i].yb;
+      tiles_out[4 * i + 3] = tiles[i].xlo;
+    }
+  }
+  if (cta_begin_out) std::copy(cta_begin.begin(), cta_begin.end(), cta_begin_out);
+  return B200CG_OK;
+}
+
 // ------------------------------------------------------------------------------------------- data movement
 long long b200cg::local_count(const b200cg_plan_s* P) { return P->g.hi - P->g.lo; }
 
