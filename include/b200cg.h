@@ -111,6 +111,7 @@ typedef struct {
   int converged;
   int stop_reason;         /* b200cg_stop */
   double r0_l2, r_l2;      /* ||r0||_2 and the recurrence ||r||_2 at exit */
+  /* the three max-norms feed the MAXNORM stop rules; under B200CG_RULE_REL_L2 r_max and dx_max may be left 0 */
   double r_max;            /* ||r||_inf (recurrence) - MSGSolver::getFinalResidualNorm */
   double dx_max;           /* ||x_n - x_{n-1}||_inf  - MSGSolver::getFinalPrecision */
   double err_max;          /* ||x - u||_inf          - MSGSolver::getFinalErrorNorm (DBL_MAX without u) */

@@ -106,56 +106,6 @@ static __global__ void finalize_kernel(DevState* st, CbRecord* log, int which, i
   }
 }
 
-// Peer-memory path: wait until every rank's publication of this epoch has landed in OUR PeerSync block, reduce the
-// slots in rank order (identical on every rank) and form the scalars. which: 1 = dot phase, 2 = update phase.
-// One warp: lane r watches rank r. A flag that does not arrive within PEER_TIMEOUT_NS ends the solve with comm_error.
-constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
-static __global__ void peer_finalize_kernel(DevState* st, CbRecord* log, const PeerLinks* pl, int which, int flags) {
-  const int lane = threadIdx.x;
-  if (st->done) return;
-  const int phase = which - 1;
-  const unsigned long long epoch = st->epoch[phase] + 1ull;
-  const PeerSync* mine = pl->sync[pl->rank];
-  bool ok = true;
-  if (lane < pl->world) {
-    const volatile unsigned long long* f = &mine->flag[phase][lane];
-    const unsigned long long t0 = global_ns();
-    while (*f < epoch) {
-      if (global_ns() - t0 > PEER_TIMEOUT_NS) {
-        ok = false;
-        break;
-      }
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  __threadfence_system();
-  if (lane != 0) return;
-  st->epoch[phase] = epoch;
-  if (!ok) {
-    st->comm_error = 1;
-    st->done = 1;
-    st->converged = 0;
-    return;
-  }
-  double s[4] = {0.0, 0.0, 0.0, 0.0}, mx[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int r = 0; r < pl->world; ++r) {
-    const volatile double* v = mine->vals[phase][r];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      s[k] += v[k];
-      mx[k] = fmax(mx[k], v[4 + k]);
-    }
-  }
-  const bool has_u = (flags & F_U) != 0, report = (flags & F_REPORT) != 0;
-  if (which == 1) {
-    finalize_dot(st, s[0], s[1]);
-  } else {
-    finalize_update(st, log, s[0], mx[0], mx[1], has_u ? mx[2] : DBL_MAX, report ? s[1] : 0.0,
-                    (report && has_u) ? s[2] : 0.0, report);
-    note_x_deferral(st, flags);
-  }
-}
-
 // x += alpha_prev * p over the owned rows: settles the update an even (NOX) last iteration left pending.
 static __global__ void __launch_bounds__(CTA_THREADS) x_flush_kernel(double* __restrict__ x, const double* __restrict__ p,
                                                              DevState* st, size_t begin, size_t count) {

@@ -252,4 +252,51 @@ __device__ __forceinline__ void finalize_update(DevState* st, CbRecord* log, dou
   }
 }
 
+// Peer-memory path, second half (same thread, right after peer_publish): wait until every rank's publication of
+// this epoch has landed in OUR PeerSync block, reduce the slots in rank order (identical on every rank) and form the
+// scalars. which: 1 = dot phase, 2 = update phase. Every rank publishes before it waits, so the wait cannot
+// deadlock; a flag that does not arrive within PEER_TIMEOUT_NS ends the solve with comm_error.
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void peer_finalize(DevState* st, CbRecord* log, const PeerLinks* pl, int which, int flags) {
+  const int phase = which - 1;
+  const unsigned long long epoch = st->epoch[phase] + 1ull;
+  const PeerSync* mine = pl->sync[pl->rank];
+  bool ok = true;
+  const unsigned long long t0 = global_ns();
+  for (int r = 0; r < pl->world && ok; ++r) {
+    const volatile unsigned long long* f = &mine->flag[phase][r];
+    while (*f < epoch) {
+      if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+        ok = false;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  st->epoch[phase] = epoch;
+  if (!ok) {
+    st->comm_error = 1;
+    st->done = 1;
+    st->converged = 0;
+    return;
+  }
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, mx[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < pl->world; ++r) {
+    const volatile double* v = mine->vals[phase][r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[k] += v[k];
+      mx[k] = fmax(mx[k], v[4 + k]);
+    }
+  }
+  const bool has_u = (flags & F_U) != 0, report = (flags & F_REPORT) != 0;
+  if (which == 1) {
+    finalize_dot(st, s[0], s[1]);
+  } else {
+    finalize_update(st, log, s[0], mx[0], mx[1], has_u ? mx[2] : DBL_MAX, report ? s[1] : 0.0,
+                    (report && has_u) ? s[2] : 0.0, report);
+    note_x_deferral(st, flags);
+  }
+}
+
 }  // namespace b200cg

@@ -78,10 +78,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     }
     rc = launch_tile<MODE_DOT, 0>(P, a, s);
     ++kernels;
-    if (rc == B200CG_OK && peer) {
-      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 1, fl);
-      ++kernels;
-    } else if (rc == B200CG_OK && P->desc.world > 1) {
+    if (rc == B200CG_OK && !peer && P->desc.world > 1) {  // (peer memory: the sweep's last CTA did it)
       rc = reduce_and_finalize(P, 1, fl, false, s);
       ++kernels;
     }
@@ -94,10 +91,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     else if (with_u) rc = launch_tile<MODE_UPD, F_U>(P, a, s);
     else rc = launch_tile<MODE_UPD, 0>(P, a, s);
     ++kernels;
-    if (rc == B200CG_OK && peer) {
-      peer_finalize_kernel<<<1, 32, 0, s>>>(P->d_state, P->d_log, P->d_links, 2, fl);
-      ++kernels;
-    } else if (rc == B200CG_OK && P->desc.world > 1) {
+    if (rc == B200CG_OK && !peer && P->desc.world > 1) {
       rc = reduce_and_finalize(P, 2, fl, /*with_max=*/!xdefer, s);
       ++kernels;
       if (rc == B200CG_OK) rc = exchange_halo2(P, P->r[par ^ 1], P->p[par ^ 1]);

@@ -12,6 +12,7 @@
 // tile order is the producer's business alone: it walks the list of equal-work tiles the host dealt to this CTA.
 #pragma once
 #include <cuda/std/cstdint>
+#include <cuda/std/type_traits>
 #include "kernels_common.cuh"
 
 namespace b200cg {
@@ -74,7 +75,9 @@ struct StreamCfg {
   static constexpr bool REPORT = (FLAGS & F_REPORT) != 0;
   static constexpr int NSTREAM = 1 + (LOAD_R ? 1 : 0) + (LOAD_X ? 1 : 0) + (LOAD_U ? 1 : 0);
   static constexpr int NS = (MODE == MODE_DOT) ? 2 : (MODE == MODE_UPD ? (REPORT ? 3 : 1) : (REPORT ? 2 : 0));
-  static constexpr int NM = (MODE == MODE_UPD) ? (LOAD_U ? 3 : 2) : 0;
+  // max-norms (|r|, |dx|, |x - u|) feed the MAXNORM stop rules only; the x-deferral flavours exist only under REL_L2
+  static constexpr bool DEFERRAL = (FLAGS & (F_NOX | F_X2)) != 0;
+  static constexpr int NM = (MODE == MODE_UPD && !DEFERRAL) ? (LOAD_U ? 3 : 2) : 0;
 };
 
 template <int MODE, int FLAGS, int HS, int NST>
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
 
   double acc_s[NS > 0 ? NS : 1] = {0.0};
   double acc_m[NM > 0 ? NM : 1] = {0.0};
+  bool sent_halo = false;  // this thread stored into a neighbour rank's halo row (peer memory)
 
   if (warp == CONS_WARPS) {
     // ================================================================ producer
@@ -184,6 +188,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
     const size_t pitch = (size_t)g.pitch;
     const bool is_out = (tid >= STRIP_HALO / 2) && (tid < CONS_THREADS - STRIP_HALO / 2);
     const int c2 = 2 * tid;  // column inside the strip
+    // the one staged column a warp-edge lane needs from outside its warp (other lanes: any valid column)
+    const int c_edge = (lane == 0) ? max(c2 - 1, 0) : ((lane == 31) ? min(c2 + 2, STRIP_LOAD - 1) : c2);
 
     int stage = 0;
     uint32_t phase = 0;
@@ -209,16 +215,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
         pm = pc = make_double2(0.0, 0.0);
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
-#pragma unroll
-      for (int j = 0; j < HS; ++j) {
-        if (j >= m.nrows) break;
+      // One staged row. full_tag: every row of the stage is an interior row of its tile (emit always, x and u
+      // staged), so the per-row predicates fold away.
+      auto do_row = [&](const int j, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const int y = m.y0 + j;
         const double* prow = sd + OFF_P + j * STRIP_LOAD;
         const double* rrow = sd + OFF_R + j * STRIP_LOAD;
         const double2 cur_p = *reinterpret_cast<const double2*>(prow + c2);
         double2 cur_r = make_double2(0.0, 0.0), cur_x = make_double2(0.0, 0.0), cur_u = make_double2(0.0, 0.0);
         if (LOAD_R) cur_r = *reinterpret_cast<const double2*>(rrow + c2);
-        const bool inner = (y >= ya) && (y < m.yb);
+        const bool inner = FULL || ((y >= ya) && (y < m.yb));
         if (LOAD_X && inner) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + c2);
         if (LOAD_U && inner) cur_u = *reinterpret_cast<const double2*>(sd + OFF_U + j * STRIP_LOAD + c2);
         // direction of this row: p = r + beta * p_old (matrix_free_system.cpp:436-438)
@@ -229,25 +236,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
           pn.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
           pn.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
         }
-        // horizontal neighbours: shuffle inside the warp, warp-edge lanes recompute from the staged rows
+        // horizontal neighbours: shuffle inside the warp; a warp-edge lane recomputes the one it lacks from the
+        // staged rows (branch-free: every lane loads some column; the strip's two outermost threads, which have no
+        // such neighbour, are halo threads whose results are masked below)
+        double pe = prow[c_edge];
+        if (MODE != MODE_APPLY) pe = __dadd_rn(rrow[c_edge], __dmul_rn(beta, pe));
         double L = __shfl_up_sync(0xffffffffu, pn.y, 1);
         double R = __shfl_down_sync(0xffffffffu, pn.x, 1);
-        if (lane == 0) {
-          L = 0.0;
-          if (tid > 0) {
-            const double pl = prow[c2 - 1];
-            L = (MODE == MODE_APPLY) ? pl : __dadd_rn(rrow[c2 - 1], __dmul_rn(beta, pl));
-          }
-        }
-        if (lane == 31) {
-          R = 0.0;
-          if (tid < CONS_THREADS - 1) {
-            const double pr = prow[c2 + 2];
-            R = (MODE == MODE_APPLY) ? pr : __dadd_rn(rrow[c2 + 2], __dmul_rn(beta, pr));
-          }
-        }
+        L = (lane == 0) ? pe : L;
+        R = (lane == 31) ? pe : R;
 
-        if (y > ya) {
+        if (FULL || y > ya) {
           // emit row y-1: centre pc, bottom pm, top pn; accumulation order diag, left, right, top, bottom
           // (matrix_free_system.cpp:216-266), each term a rounded multiply then a rounded add.
           double ap0 = __dmul_rn(cA, pc.x);
@@ -288,24 +287,29 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
               if (!NOX) st2_out(a.x + eoff, xn);
               st2_out(a.r_out + eoff, rn);
               st2_out(a.p_out + eoff, make_double2(p0, p1));
-              // peer-memory halo: the slab's first / last row also lands in the neighbour's halo row (NVLink stores)
+              // peer-memory halo: the slab's first / last row also lands in the neighbour's halo row (NVLink stores).
+              // Those rows are emitted by the first / last stage of a tile, never by a FULL stage.
               const int ye = y - 1;
               const int cs = m.col0 + c2;
-              if (a.nb_r_below && ye == g.ylo) {
+              if (!FULL && a.nb_r_below && ye == g.ylo) {
                 st2(a.nb_r_below + cs, rn);
                 st2(a.nb_p_below + cs, make_double2(p0, p1));
+                sent_halo = true;
               }
-              if (a.nb_r_above && ye == g.yhi - 1) {
+              if (!FULL && a.nb_r_above && ye == g.yhi - 1) {
                 st2(a.nb_r_above + cs, rn);
                 st2(a.nb_p_above + cs, make_double2(p0, p1));
+                sent_halo = true;
               }
             }
             acc_s[0] = fma(rn.x, rn.x, acc_s[0]);
             acc_s[0] = fma(rn.y, rn.y, acc_s[0]);
-            acc_m[0] = fmax(acc_m[0], fmax(fabs(rn.x), fabs(rn.y)));
             const double d0 = __dsub_rn(xn.x, xo0);  // msg_solver.cpp:124-129
             const double d1 = __dsub_rn(xn.y, xo1);
-            acc_m[1] = fmax(acc_m[1], fmax(fabs(d0), fabs(d1)));
+            if (NM > 0) {
+              acc_m[0] = fmax(acc_m[0], fmax(fabs(rn.x), fabs(rn.y)));
+              acc_m[NM > 1 ? 1 : 0] = fmax(acc_m[NM > 1 ? 1 : 0], fmax(fabs(d0), fabs(d1)));
+            }
             if (REPORT) {
               acc_s[1] = fma(d0, d0, acc_s[1]);
               acc_s[1] = fma(d1, d1, acc_s[1]);
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
             if (LOAD_U) {
               const double e0 = v0 ? __dsub_rn(xn.x, u_prev.x) : 0.0;  // msg_solver.cpp:132-139
               const double e1 = v1 ? __dsub_rn(xn.y, u_prev.y) : 0.0;
-              acc_m[NM - 1] = fmax(acc_m[NM - 1], fmax(fabs(e0), fabs(e1)));
+              acc_m[NM > 0 ? NM - 1 : 0] = fmax(acc_m[NM > 0 ? NM - 1 : 0], fmax(fabs(e0), fabs(e1)));
               if (REPORT) {
                 acc_s[2] = fma(e0, e0, acc_s[2]);
                 acc_s[2] = fma(e1, e1, acc_s[2]);
@@ -353,6 +357,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
         x_prev = cur_x;
         u_prev = cur_u;
         if (X2) q_prev = cur_p;
+      };
+      if (m.nrows == HS && !(m.flags & META_TILE_FIRST) && m.y0 + HS <= m.yb) {
+#pragma unroll
+        for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < m.nrows; ++j) do_row(j, cuda::std::false_type{});
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -362,12 +373,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
 
   // end of this CTA's sweep: the first consumer warp is as good a witness as any (all finish within a stage)
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
-  if (MODE == MODE_UPD && a.defer == 2) __threadfence_system();  // remote halo stores before the exit ticket
+  if (MODE == MODE_UPD && sent_halo) __threadfence_system();  // remote halo stores before the exit ticket
   if (NS + NM == 0) return;
   if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
   // ---- one thread: turn the totals into the next scalars
-  if (a.defer == 2) {
+  if (a.defer == 2) {  // peer memory: publish this rank's totals to every rank, then collect everyone's
     peer_publish<NS, NM>(a.peers, st, MODE == MODE_DOT ? 0 : 1, acc_s, acc_m);
+    peer_finalize(st, a.cb_log, a.peers, MODE == MODE_DOT ? 1 : 2, FLAGS);
     return;
   }
   if (a.defer) {
@@ -381,7 +393,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
   if (MODE == MODE_DOT) {
     finalize_dot(st, acc_s[0], acc_s[1]);
   } else if (MODE == MODE_UPD) {
-    finalize_update(st, a.cb_log, acc_s[0], acc_m[0], acc_m[1], LOAD_U ? acc_m[NM - 1] : DBL_MAX,
+    finalize_update(st, a.cb_log, acc_s[0], NM > 0 ? acc_m[0] : 0.0, NM > 1 ? acc_m[NM > 1 ? 1 : 0] : 0.0,
+                    LOAD_U ? acc_m[NM > 0 ? NM - 1 : 0] : DBL_MAX,
                     REPORT ? acc_s[1] : 0.0, (REPORT && LOAD_U) ? acc_s[2] : 0.0, REPORT);
     note_x_deferral(st, FLAGS);
   } else if (REPORT) {
