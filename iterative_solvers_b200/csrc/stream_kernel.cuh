@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
               st2_out(a.r_out + eoff, rn);
               st2_out(a.p_out + eoff, make_double2(p0, p1));
               // peer-memory halo: the slab's first / last row also lands in the neighbour's halo row (NVLink stores).
-              // Those rows are emitted by the first / last stage of a tile, never by a FULL stage.
+              // Those are a tile's first / last emit rows, which a FULL stage never holds.
               const int ye = y - 1;
               const int cs = m.col0 + c2;
               if (!FULL && a.nb_r_below && ye == g.ylo) {
@@ -358,7 +358,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
         u_prev = cur_u;
         if (X2) q_prev = cur_p;
       };
-      if (m.nrows == HS && !(m.flags & META_TILE_FIRST) && m.y0 + HS <= m.yb) {
+      // FULL: rows y0 .. y0+HS-1 all in [ya, yb) and the emitted rows y0-1 .. y0+HS-2 all in (ya, yb-1), so neither
+      // the tile's first emit row (a slab's first row goes to the neighbour's halo) nor its last is handled here
+      if (m.nrows == HS && !(m.flags & META_TILE_FIRST) && m.y0 - 1 > m.ya && m.y0 + HS <= m.yb) {
 #pragma unroll
         for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
       } else {

@@ -28,21 +28,32 @@ def main():
         return bytes(blob.cpu().tolist())
 
     failures = []
+    # "mf-hs2": every sweep flavour with 2-row stages (the launch shapes are read when the plan is created);
+    # "msg0": the max-norm rules without a true solution
+    hs2 = {"B200CG_SHAPE_DOT": "0", "B200CG_SHAPE_UPD": "0", "B200CG_SHAPE_NOX": "0"}
     for n, domain, eps, kind in [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
-                                 (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "cb")]:
+                                 (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"),
+                                 (128, 0, 1e-8, "cb")]:
         o = Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
         b, u = o.rhs(), o.true_solution()
+        if kind == "mf-hs2":
+            os.environ.update(hs2)
         plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local, rank=rank, world=world,
                          comm_id=fresh_comm_id())
+        for k in hs2:
+            os.environ.pop(k, None)
         lo, hi = plan.lo, plan.hi
         got_cb = []
-        if kind == "mf":
+        if kind in ("mf", "mf-hs2"):
             ref = o.mf_solve(b=b, eps=eps, max_it=20000)
             x, info = plan.solve(b=b[lo:hi], eps_rel=eps, max_it=20000)
         elif kind == "cb":
             ref = o.mf_solve(b=b, eps=eps, max_it=20000, with_hist=True)
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], eps_rel=eps, max_it=20000,
                                  callback=lambda it, p, r, e: got_cb.append((it, p, r, e)))
+        elif kind == "msg0":
+            ref = o.msg_solve(b=b, eps_p=eps, eps_r=eps, max_it=20000)
+            x, info = plan.solve(b=b[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
         else:
             ref = o.msg_solve(b=b, u=u, eps_p=eps, eps_r=eps, max_it=20000)
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
@@ -60,7 +71,7 @@ def main():
             ok = abs(info["iterations"] - ref["iterations"]) <= 1 and rel < 1e-10
             ok = ok and np.array_equal(yg, o.apply(v))
             ok = ok and np.max(np.abs(rg - (o.apply(xg) - b))) <= 1e-12 * np.max(np.abs(b))
-            if kind == "msg":
+            if kind in ("msg", "msg0"):
                 ok = ok and info["stop_reason"] == ref["stop_reason"]
             if kind == "cb":
                 got = np.array(got_cb)
