@@ -52,6 +52,8 @@ def parse_args():
                          "(BASELINE.json configs[2])")
     ap.add_argument("--domain", default="lshape", choices=["lshape", "rect"])
     ap.add_argument("--op", default="mf", choices=["mf", "csr"])
+    ap.add_argument("--single-sweep", type=int, default=0, choices=[0, 1, 2],
+                    help="b200cg_params.single_sweep: 1 = one sweep per iteration (Chronopoulos-Gear alpha), 0 = plan default")
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--iters-per-graph", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -243,7 +245,8 @@ def run_b200(args):
     if op == capi.OP_CSR:
         plan.assemble_csr()
     n_local = plan.n_local
-    solve_kw = dict(op=op, rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=args.iters, iters_per_graph=args.iters_per_graph)
+    solve_kw = dict(op=op, rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=args.iters, iters_per_graph=args.iters_per_graph,
+                    single_sweep=args.single_sweep)
 
     # ---- value: inputs resident in HBM
     for _ in range(args.warmup):
@@ -252,7 +255,7 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, dot_ms, upd_ms, samples, its_done = 0.0, 0, 0.0, 0.0, 0, 0
-    upd_even_ms, upd_odd_ms, xdefer, peer_exchange = 0.0, 0.0, 0, 0
+    upd_even_ms, upd_odd_ms, xdefer, peer_exchange, single_sweep = 0.0, 0.0, 0, 0, 0
     for _ in range(args.steps):
         _, info = plan.solve(rhs_on_device=True, keep_x_on_device=True, **solve_kw)
         dev_ms += info["device_ms"]
@@ -264,6 +267,7 @@ def run_b200(args):
             upd_even_ms += info["upd_even_ms"]
             upd_odd_ms += info["upd_odd_ms"]
             xdefer = info["x_deferral"]
+            single_sweep = info["single_sweep"]
             peer_exchange = info["peer_exchange"]
             samples += 1
     barrier()
@@ -319,17 +323,21 @@ def run_b200(args):
         achieved = BYTES_UPD * n_local / upd_s / 1e9
         even_bytes = BYTES_UPD_NOX if xdefer else BYTES_UPD
         iter_s = dot_s + 0.5 * (upd_s + nox_s)
-        roofline = {"bound": "hbm", "kernel": "cg_stream_kernel<MODE_UPD> (update phase touching x)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+        roofline = {"bound": "hbm",
+                    "kernel": ("cg_fused_kernel<F_X2> (single-sweep iteration touching x)" if single_sweep
+                               else "cg_stream_kernel<MODE_UPD> (update phase touching x)"), "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None if single_sweep else ncu_traffic(),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_UPD * n_local,
                     "avg_launch_ms": upd_s * 1e3, "launches_sampled": samples,
                     "x_deferral": bool(xdefer),
                     "update_kernel_even_iterations": {"achieved": even_bytes * n_local / nox_s / 1e9 if nox_s > 0 else None,
                                                       "avg_launch_ms": nox_s * 1e3,
                                                       "algorithmic_bytes_per_launch": even_bytes * n_local},
-                    "dot_kernel": {"achieved": BYTES_DOT * n_local / dot_s / 1e9 if dot_s > 0 else None,
+                    "dot_kernel": None if single_sweep else
+                                  {"achieved": BYTES_DOT * n_local / dot_s / 1e9 if dot_s > 0 else None,
                                    "avg_launch_ms": dot_s * 1e3, "algorithmic_bytes_per_launch": BYTES_DOT * n_local},
-                    "algorithmic_bytes_per_dof_iter": BYTES_DOT + 0.5 * (BYTES_UPD + even_bytes),
+                    "single_sweep": bool(single_sweep),
+                    "algorithmic_bytes_per_dof_iter": (0.0 if single_sweep else BYTES_DOT) + 0.5 * (BYTES_UPD + even_bytes),
                     "kernel_share_of_step": iter_s * 1e3 * (its_done / max(args.steps, 1)) /
                                             (dev_ms / max(args.steps, 1))}
     cpu_baseline = None

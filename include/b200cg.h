@@ -103,7 +103,13 @@ typedef struct {
   int small_grid_path;     /* grids that fit the shared memory of one thread-block cluster (about 300^2) are solved by
                               a single cluster-resident kernel instead of the graph loop: 0 = automatic, 1 = never,
                               2 = require it (B200CG_ERR_UNSUPPORTED if the grid does not fit) */
-  int reserved[6];
+  int single_sweep;        /* matrix-free, RULE_REL_L2, no callback, unsharded plan: 1 = run each iteration as ONE sweep
+                              (40 instead of 56 bytes per unknown) by forming alpha from the single-reduction CG
+                              recurrence (Chronopoulos-Gear) instead of p.Ap - the same iterates in exact arithmetic,
+                              <= 4e-14 relative apart in fp64 on the reference's grids
+                              (scripts/study_single_reduction_cg.py). 0 = the plan's default (off unless
+                              B200CG_SINGLE_SWEEP=1), 2 = never. Ignored where it does not apply */
+  int reserved[5];
 } b200cg_params;
 
 typedef struct {
@@ -131,7 +137,8 @@ typedef struct {
   int cluster_path;        /* 1 if this solve ran as one cluster-resident kernel (small_grid_path) */
   int peer_exchange;       /* sharded plans: 1 if halo rows and reductions went over NVLink peer memory (CUDA IPC),
                               0 if over NCCL send/recv + all-reduce */
-  int reserved[3];
+  int single_sweep;        /* 1 if this solve ran the single-sweep iteration (b200cg_params.single_sweep) */
+  int reserved[2];
 } b200cg_info;
 
 /* (iteration, precision, residual, error) - Solver::setIterationCallback, solver.hpp:46-50. Called on the
@@ -166,7 +173,9 @@ int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_hi, int64_t
  * 512-column strip starting at storage column col0, emit rows [ya, yb), first unknown x of these rows; it writes the
  * unknowns x in [max(col0, xlo), min(col0 + 503, n - 1)]. CTA c walks tiles [cta_begin[c], cta_begin[c + 1]).
  * weights (n_weights entries, or NULL for the initial equal split) are the per-CTA shares feedback balancing
- * converges to. tiles holds `capacity` quadruples, cta_begin sms * ctas_per_sm + 1 ints. */
+ * converges to. tiles holds `capacity` quadruples, cta_begin sms * ctas_per_sm + 1 ints. desc->reserved0 = 1 asks
+ * for the single-sweep kernel's strips instead: 484 staged columns from storage column col0 = strip * 480 + 2, writing
+ * x in [max(col0 - 2, xlo), min(col0 + 477, n - 1)]. */
 int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas_per_sm, const double* weights, int n_weights,
                       int* tiles, int64_t capacity, int64_t* n_tiles, int* cta_begin, int* grid);
 
@@ -207,7 +216,7 @@ int b200cg_solve(b200cg_plan_t plan, const b200cg_params* params, const double* 
  * (dirichlet_solver.cpp:147-180). Either output may be NULL. op selects the stencil or the CSR matrix. */
 int b200cg_postprocess(b200cg_plan_t plan, int op, double* residual_host, double* error_host);
 /* Diagnostics: start/end time stamps (ns, device global timer) of every persistent CTA in the last launch of a sweep
- * kernel flavour (0 = dot phase, 1 = update phase without x, 2 = update phase with x). out receives 2 * (*n_ctas)
+ * kernel flavour (0 = dot phase, 1 = update phase without x, 2 = update phase with x, 3 = single-sweep iteration). out receives 2 * (*n_ctas)
  * values; capacity is the number of pairs out can hold. */
 int b200cg_cta_times(b200cg_plan_t plan, int flavour, uint64_t* out, int capacity, int* n_ctas);
 /* copy the device-resident solution of the last solve (keep_x_on_device) to the host */

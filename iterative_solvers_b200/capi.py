@@ -43,7 +43,7 @@ class Params(C.Structure):
     _fields_ = [("op", C.c_int), ("rule", C.c_int), ("eps_rel", C.c_double), ("eps_p", C.c_double),
                 ("eps_r", C.c_double), ("eps_e", C.c_double), ("max_it", C.c_int), ("callback_every", C.c_int),
                 ("rhs_on_device", C.c_int), ("keep_x_on_device", C.c_int), ("iters_per_graph", C.c_int),
-                ("small_grid_path", C.c_int), ("reserved", C.c_int * 6)]
+                ("small_grid_path", C.c_int), ("single_sweep", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class SolveInfo(C.Structure):
@@ -54,7 +54,8 @@ class SolveInfo(C.Structure):
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("dot_kernel_ms", C.c_double),
                 ("upd_kernel_ms", C.c_double), ("kernel_samples", C.c_int), ("local_unknowns", C.c_int64),
                 ("upd_even_ms", C.c_double), ("upd_odd_ms", C.c_double), ("x_deferral", C.c_int),
-                ("cluster_path", C.c_int), ("peer_exchange", C.c_int), ("reserved", C.c_int * 3)]
+                ("cluster_path", C.c_int), ("peer_exchange", C.c_int), ("single_sweep", C.c_int),
+                ("reserved", C.c_int * 2)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -129,11 +130,13 @@ def partition(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1):
     return ylo.value, yhi.value, lo.value, hi.value, N.value
 
 
-def work_split(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1, sms=148, ctas_per_sm=2, weights=None, tile_rows=0):
+def work_split(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1, sms=148, ctas_per_sm=2, weights=None, tile_rows=0,
+               fused=False):
     """The sweep kernels' tile table for such a plan: (tiles[k, 4] = col0, ya, yb, xlo; cta_begin[grid + 1]).
+    fused: the single-sweep kernel's strip geometry (480 written columns from storage column strip * 480 + 2).
     Pure host logic (b200cg_work_split) - works without a GPU."""
     desc = PlanDesc(n=int(n), m=int(m), a=0.0, b=1.0, c=0.0, d=1.0, domain=int(domain), device=0, rank=int(rank),
-                    world=int(world), tile_rows=int(tile_rows))
+                    world=int(world), tile_rows=int(tile_rows), reserved0=1 if fused else 0)
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     nw = 0 if w is None else int(w.size)
     count, grid = C.c_int64(), C.c_int()
@@ -273,12 +276,12 @@ class Plan:
     # ---- solve
     def solve(self, b=None, u=None, x_out=None, op=OP_MATRIX_FREE, rule=RULE_REL_L2, eps_rel=1e-6, eps_p=-1.0,
               eps_r=-1.0, eps_e=-1.0, max_it=10000, callback=None, callback_every=100, rhs_on_device=False,
-              keep_x_on_device=False, iters_per_graph=0, stop_flag=None, small_grid_path=0):
+              keep_x_on_device=False, iters_per_graph=0, stop_flag=None, small_grid_path=0, single_sweep=0):
         """Returns (x, info dict). b / u / x_out may be numpy arrays or PinnedArray.array views."""
         prm = Params(op=op, rule=rule, eps_rel=eps_rel, eps_p=eps_p, eps_r=eps_r, eps_e=eps_e, max_it=int(max_it),
                      callback_every=int(callback_every), rhs_on_device=int(bool(rhs_on_device)),
                      keep_x_on_device=int(bool(keep_x_on_device)), iters_per_graph=int(iters_per_graph),
-                     small_grid_path=int(small_grid_path))
+                     small_grid_path=int(small_grid_path), single_sweep=int(single_sweep))
         if b is not None:
             b = np.ascontiguousarray(b, dtype=np.float64)
             assert b.shape == (self.n_local,)

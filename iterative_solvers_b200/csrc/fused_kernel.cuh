@@ -1,0 +1,297 @@
+// Single-sweep CG iteration (sm_100a): one kernel per iteration, 40 B per unknown instead of 56.
+//
+// The two-sweep scheme (stream_kernel.cuh) needs p.Ap before it may update r, hence two passes over r and p.
+// Here alpha comes from the recurrence of the single-reduction CG (Chronopoulos & Gear):
+//
+//     gamma_k = r_k.r_k,   delta_k = r_k.A r_k,   beta_k = gamma_k / gamma_{k-1},
+//     alpha_k = gamma_k / (delta_k - beta_k gamma_k / alpha_{k-1})          (= gamma_k / p_k.A p_k in exact arithmetic)
+//
+// so that one pass can do   p = r + beta p_old,  x += alpha p,  r' = r - alpha A p,  gamma' = r'.r',  delta' = r'.A r'.
+// A r' needs r' at the four neighbours, i.e. A p one node further out, i.e. p two nodes out: the sweep carries a halo
+// of two rows / two columns and recomputes p and r' there. Element-wise arithmetic is unchanged (separately rounded
+// multiply/add in the reference's order, matrix_free_system.cpp:216-266, :422-438); only the way alpha is formed
+// differs, and scripts/study_single_reduction_cg.py shows the iterates stay within 4e-14 of the reference's on every
+// golden grid (same iteration counts). Opt-in (b200cg_params.single_sweep / B200CG_SINGLE_SWEEP), REL_L2 rule,
+// unsharded plans.
+//
+// Structure: the producer warp / mbarrier stage ring of stream_kernel.cuh. Consumers differ in the column mapping:
+// every warp owns a window of 64 staged columns and writes the inner 60, so all horizontal neighbours (two levels)
+// come from warp shuffles and no lane needs another warp's data: 8 warps x 60 = 480 written columns per strip of
+// 484 staged ones. Rows run through a two-deep register pipeline: when row y arrives, A p and r' of row y-1 and
+// A r' of row y-2 become computable.
+#pragma once
+#include "stream_kernel.cuh"
+
+namespace b200cg {
+
+constexpr int FUSED_STRIP_OUT = 480;    // columns written per strip
+constexpr int FUSED_STRIP_COLS = 484;   // columns staged: two halo columns per side
+constexpr int FUSED_COL_SHIFT = 2;      // a strip's first staged storage column is strip * FUSED_STRIP_OUT + this
+constexpr int FUSED_WARP_STEP = 60;     // columns written per consumer warp (64 processed)
+
+template <int FLAGS>
+struct FusedCfg {
+  static constexpr bool X2 = (FLAGS & F_X2) != 0;   // odd iteration: x += alpha_prev * p_old + alpha * p
+  static constexpr bool NOX = !X2;                  // even iteration: x untouched, its update stays pending
+  static constexpr int NSTREAM = X2 ? 3 : 2;        // p, r, [x]
+};
+
+template <int FLAGS, int HS, int NST>
+constexpr size_t fused_smem_bytes() {
+  return (size_t)NST * HS * FusedCfg<FLAGS>::NSTREAM * ROW_BYTES + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
+}
+
+// The scalars of the next iteration from gamma' = r'.r' and delta' = r'.A r' (one thread, after the grid reduction).
+// Stop test as MatrixFreeSolver's (matrix_free_system.cpp:409, :432-441).
+__device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, double delta_new, int flags) {
+  const int it = st->it + 1;
+  st->it = it;
+  const double r_norm = sqrt(gamma_new);
+  st->r_norm = r_norm;
+  st->r_max = 0.0;
+  st->dx_max = 0.0;
+  note_x_deferral(st, flags);  // remembers this iteration's alpha before it is replaced
+  const bool go = (it < st->max_it) && (r_norm > st->eps_rel * st->r0_norm);
+  if (!go) {
+    st->rr = gamma_new;
+    st->done = 1;
+    st->converged = (r_norm <= st->eps_rel * st->r0_norm) ? 1 : 0;
+    st->stop_reason = st->converged ? 2 : 0;
+    return;
+  }
+  const double beta = gamma_new / st->rr;
+  const double alpha = gamma_new / (delta_new - beta * gamma_new / st->alpha);
+  st->rr = gamma_new;
+  st->beta = beta;
+  st->alpha = alpha;
+  st->pAp = gamma_new / alpha;
+}
+
+template <int FLAGS, int HS, int NST, int CTAS>
+__global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const TileArgs a) {
+  using Cfg = FusedCfg<FLAGS>;
+  constexpr bool X2 = Cfg::X2;
+  constexpr int NSTREAM = Cfg::NSTREAM;
+  constexpr int STAGE_DOUBLES = HS * NSTREAM * STRIP_LOAD;
+  constexpr int OFF_P = 0, OFF_R = HS * STRIP_LOAD, OFF_X = 2 * HS * STRIP_LOAD;
+
+  const Geom& g = a.g;
+  DevState* st = a.st;
+  if (st->done) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage_data = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + NST;
+  StageMeta* meta = reinterpret_cast<StageMeta*>(empty + NST);
+  __shared__ double scratch[2 * 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], CONS_WARPS);
+    }
+    mbar_fence_init();
+    if (a.cta_clock) a.cta_clock[2 * blockIdx.x] = global_ns();
+  }
+  __syncthreads();
+
+  double acc_s[2] = {0.0, 0.0};  // gamma', delta'
+  double acc_m[1] = {0.0};
+  const int y_store_lo = g.ybase, y_store_hi = g.ybase + g.yrows;  // stored rows [lo, hi)
+
+  if (warp == CONS_WARPS) {
+    // ================================================================ producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t pitch = (size_t)g.pitch;
+      const int t_end = a.cta_begin[blockIdx.x + 1];
+      for (int t = a.cta_begin[blockIdx.x]; t < t_end; ++t) {
+        const Tile tl = a.tiles[t];
+        const int col0 = tl.col0, ya = tl.ya, yb = tl.yb;
+        const uint32_t row_bytes = (uint32_t)min(FUSED_STRIP_COLS, g.pitch - col0) * 8u;
+        const int S = yb - ya + 4;  // rows ya-2 .. yb+1
+        for (int s0 = 0; s0 < S; s0 += HS) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const int nrows = min(HS, S - s0);
+          const int y0 = ya - 2 + s0;
+          StageMeta m;
+          m.col0 = col0; m.y0 = y0; m.nrows = nrows; m.flags = (s0 == 0) ? META_TILE_FIRST : 0;
+          m.ya = ya; m.yb = yb; m.xlo = tl.xlo; m.pad = 0;
+          meta[stage] = m;
+          // rows outside the stored range (below the first / above the last boundary row) are not copied: the
+          // consumers take them as zeros. Emit rows also need x.
+          int stored = 0, inner = 0;
+          for (int j = 0; j < nrows; ++j) {
+            const int y = y0 + j;
+            stored += (y >= y_store_lo && y < y_store_hi) ? 1 : 0;
+            inner += (y >= ya && y < yb) ? 1 : 0;
+          }
+          const uint32_t bytes = row_bytes * (uint32_t)(2 * stored + (X2 ? inner : 0));
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
+          for (int j = 0; j < nrows; ++j) {
+            const int y = y0 + j;
+            if (y < y_store_lo || y >= y_store_hi) continue;
+            const size_t off = (size_t)(y - g.ybase) * pitch + (size_t)col0;
+            bulk_g2s(sd + OFF_P + j * STRIP_LOAD, a.p_in + off, row_bytes, &full[stage]);
+            bulk_g2s(sd + OFF_R + j * STRIP_LOAD, a.r_in + off, row_bytes, &full[stage]);
+            if (X2 && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * STRIP_LOAD, a.x + off, row_bytes, &full[stage]);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+      mbar_wait(&empty[stage], phase ^ 1u);
+      StageMeta m;
+      m.col0 = 0; m.y0 = 0; m.nrows = 0; m.flags = META_END; m.ya = 0; m.yb = 0; m.xlo = 0; m.pad = 0;
+      meta[stage] = m;
+      mbar_arrive(&full[stage]);
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ consumers
+    const double cA = g.A, cxk = g.xk, cyk = g.yk;
+    const double beta = st->beta, alpha = st->alpha;
+    double alpha_prev = 0.0;
+    if (X2) alpha_prev = st->alpha_prev;
+    const size_t pitch = (size_t)g.pitch;
+    const int sc = FUSED_WARP_STEP * warp + 2 * lane;   // this thread's first staged column
+    const bool writer = (lane >= 1) && (lane <= 30);    // lanes 0 and 31 only feed their neighbours
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    // the five-point operator at one node, accumulated in the reference's order: diag, left, right, top, bottom
+    auto stencil = [&](double c, double l, double r, double t, double b) -> double {
+      double v = __dmul_rn(cA, c);
+      v = __dadd_rn(v, __dmul_rn(cxk, l));
+      v = __dadd_rn(v, __dmul_rn(cxk, r));
+      v = __dadd_rn(v, __dmul_rn(cyk, t));
+      v = __dadd_rn(v, __dmul_rn(cyk, b));
+      return v;
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    // per-tile pipeline state; "1" = one row back, "2" = two rows back
+    int ya = 0, yb = 0, x0 = 0;
+    size_t col_off = 0;
+    double2 P1 = zero2, P2 = zero2;        // p of rows y-1, y-2
+    double LP1 = 0.0, RP1 = 0.0;           // horizontal neighbours of P1
+    double2 R1 = zero2, R2 = zero2;        // r' of rows y-2, y-3
+    double LR1 = 0.0, RR1 = 0.0;           // horizontal neighbours of R1
+    double2 r1 = zero2, x1 = zero2, q1 = zero2;  // staged r, x, p_old of row y-1 (masked)
+    bool k1a = false, k1b = false;         // row y-1: are this thread's two nodes unknowns
+    bool va = false, vb = false;           // the same for the rows of the tile itself (all in one block of the L)
+
+    for (;;) {
+      mbar_wait(&full[stage], phase);
+      const StageMeta m = meta[stage];
+      if (m.flags & META_END) break;
+      if (m.flags & META_TILE_FIRST) {
+        ya = m.ya;
+        yb = m.yb;
+        x0 = m.col0 + sc - XOFF;
+        col_off = (size_t)(m.col0 + sc);
+        P1 = P2 = R1 = R2 = r1 = x1 = q1 = zero2;
+        LP1 = RP1 = LR1 = RR1 = 0.0;
+        k1a = k1b = false;
+        va = (x0 >= m.xlo) && (x0 <= g.n - 1);
+        vb = (x0 + 1 >= m.xlo) && (x0 + 1 <= g.n - 1);
+      }
+      const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
+      // One staged row. full_tag: every row of the stage lies in [ya+2, yb), so it is stored, it is a row of the
+      // tile (masks va / vb), rows y-1 and y-2 are emit rows and x is staged: the per-row predicates fold away.
+      auto do_row = [&](const int j, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int y = m.y0 + j;
+        // ---- row y arrives: its direction p = r + beta * p_old, zero outside the unknowns
+        bool k0a, k0b;
+        double2 cur_p = zero2, cur_r = zero2, cur_x = zero2;
+        if (FULL) {
+          k0a = va;
+          k0b = vb;
+          cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * STRIP_LOAD + sc);
+          cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * STRIP_LOAD + sc);
+          if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + sc);
+        } else {
+          const bool row_stored = (y >= y_store_lo) && (y < y_store_hi);
+          const bool row_ok = (y >= 1) && (y <= g.m - 1);
+          const int xlo = (g.ysplit != 0 && y <= g.ysplit) ? g.xsplit + 1 : 1;
+          k0a = row_ok && (x0 >= xlo) && (x0 <= g.n - 1);
+          k0b = row_ok && (x0 + 1 >= xlo) && (x0 + 1 <= g.n - 1);
+          if (row_stored) {
+            cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * STRIP_LOAD + sc);
+            cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * STRIP_LOAD + sc);
+            if (X2 && y >= ya && y < yb) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + sc);
+          }
+        }
+        cur_p.x = k0a ? cur_p.x : 0.0;  cur_p.y = k0b ? cur_p.y : 0.0;
+        cur_r.x = k0a ? cur_r.x : 0.0;  cur_r.y = k0b ? cur_r.y : 0.0;
+        cur_x.x = k0a ? cur_x.x : 0.0;  cur_x.y = k0b ? cur_x.y : 0.0;
+        double2 P0;
+        P0.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
+        P0.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
+        const double LP0 = __shfl_up_sync(0xffffffffu, P0.y, 1);
+        const double RP0 = __shfl_down_sync(0xffffffffu, P0.x, 1);
+
+        // ---- row y-1: A p and r' = r - alpha A p (zero outside the unknowns)
+        double2 R0;
+        {
+          const double ap0 = stencil(P1.x, LP1, P1.y, P0.x, P2.x);
+          const double ap1 = stencil(P1.y, P1.x, RP1, P0.y, P2.y);
+          R0.x = k1a ? __dsub_rn(r1.x, __dmul_rn(alpha, ap0)) : 0.0;
+          R0.y = k1b ? __dsub_rn(r1.y, __dmul_rn(alpha, ap1)) : 0.0;
+        }
+        const bool emit1 = FULL || ((y - 1 >= ya) && (y - 1 < yb));
+        if (emit1 && writer) {
+          if (k1a || k1b) {
+            const size_t o = (size_t)(y - 1 - g.ybase) * pitch + col_off;
+            st2_out(a.r_out + o, R0);
+            st2_out(a.p_out + o, P1);
+            if (X2) {  // x += alpha_prev * p_old, then += alpha * p: the reference's order of additions
+              double2 xn;
+              xn.x = __dadd_rn(__dadd_rn(x1.x, __dmul_rn(alpha_prev, q1.x)), __dmul_rn(alpha, P1.x));
+              xn.y = __dadd_rn(__dadd_rn(x1.y, __dmul_rn(alpha_prev, q1.y)), __dmul_rn(alpha, P1.y));
+              st2_out(a.x + o, xn);
+            }
+          }
+          acc_s[0] = fma(R0.x, R0.x, acc_s[0]);
+          acc_s[0] = fma(R0.y, R0.y, acc_s[0]);
+        }
+        const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
+        const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
+
+        // ---- row y-2: A r' and delta' += r'.A r'
+        if ((FULL || ((y - 2 >= ya) && (y - 2 < yb))) && writer) {
+          const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
+          const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
+          acc_s[1] = fma(R1.x, w0, acc_s[1]);
+          acc_s[1] = fma(R1.y, w1, acc_s[1]);
+        }
+
+        // ---- shift the pipeline
+        P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
+        R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
+        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
+        k1a = k0a;  k1b = k0b;
+      };
+      if (m.nrows == HS && m.y0 >= ya + 2 && m.y0 + HS <= yb) {
+#pragma unroll
+        for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < m.nrows; ++j) do_row(j, cuda::std::false_type{});
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
+  if (!grid_reduce<2, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
+  finalize_fused(st, acc_s[0], acc_s[1], FLAGS);
+}
+
+}  // namespace b200cg

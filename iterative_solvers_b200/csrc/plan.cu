@@ -119,13 +119,14 @@ static void build_tiles(b200cg_plan_s* P, TileTable* tt, std::vector<Tile>* tile
   const Geom& g = P->g;
   struct Col { int col0, y0, y1, xlo; };
   std::vector<Col> cols;  // one entry per (block, strip)
-  const int strips = (g.n - 1) / STRIP_OUT + 1;
+  const int strip_out = tt->strip_out, shift = tt->col_shift;
+  const int strips = (g.n - 1) / strip_out + 1;
   const int yB0 = g.ylo, yB1 = g.ysplit ? std::max(g.ylo, std::min(g.yhi, g.ysplit + 1)) : g.ylo;
   const int yU0 = std::max(g.ylo, g.ysplit + 1), yU1 = std::max(yU0, g.yhi);
   if (yB1 > yB0)
-    for (int s = (g.xsplit + 1) / STRIP_OUT; s < strips; ++s) cols.push_back({s * STRIP_OUT, yB0, yB1, g.xsplit + 1});
+    for (int s = (g.xsplit + 1) / strip_out; s < strips; ++s) cols.push_back({s * strip_out + shift, yB0, yB1, g.xsplit + 1});
   if (yU1 > yU0)
-    for (int s = 0; s < strips; ++s) cols.push_back({s * STRIP_OUT, yU0, yU1, 1});
+    for (int s = 0; s < strips; ++s) cols.push_back({s * strip_out + shift, yU0, yU1, 1});
   long long total = 0;
   for (const Col& c : cols) total += c.y1 - c.y0;
   const int max_grid = P->sms * tt->ctas_per_sm;
@@ -190,7 +191,7 @@ static int upload_tiles(b200cg_plan_s* P, TileTable* tt) {
   std::vector<int> cta_begin;
   build_tiles(P, tt, &tiles, &cta_begin);
   if (!tt->d_tiles) {
-    tt->tile_capacity = tiles.size() + 4 * ((size_t)(P->g.n - 1) / STRIP_OUT + 2) + 64;  // + strip-end splits
+    tt->tile_capacity = tiles.size() + 4 * ((size_t)(P->g.n - 1) / tt->strip_out + 2) + 64;  // + strip-end splits
     CU(cudaMalloc(&tt->d_tiles, tt->tile_capacity * sizeof(Tile)));
     CU(cudaMalloc(&tt->d_cta_begin, ((size_t)P->sms * tt->ctas_per_sm + 1) * sizeof(int)));
   }
@@ -434,6 +435,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->cluster_enabled = env_int("B200CG_CLUSTER", 1) != 0;
+    P->single_sweep_default = env_int("B200CG_SINGLE_SWEEP", 0) != 0;
     if (!P->generic && P->cluster_enabled) {
       // probe once whether the non-portable 16-CTA cluster is schedulable with a full shared-memory carve-out
       cudaLaunchConfig_t cfg = {};
@@ -461,6 +463,9 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->tile_tab[0].ctas_per_sm = ctas_of(P->shape_dot);
     P->tile_tab[1].ctas_per_sm = ctas_of(P->shape_nox);
     P->tile_tab[2].ctas_per_sm = 2;  // every other flavour runs a 2-CTAs/SM shape
+    P->tile_tab[3].ctas_per_sm = 2;  // single-sweep iteration: its own strip geometry (fused_kernel.cuh)
+    P->tile_tab[3].strip_out = FUSED_STRIP_OUT;
+    P->tile_tab[3].col_shift = FUSED_COL_SHIFT;
     if (P->shape_upd == 1) P->shape_upd = 0;
     for (auto& tt : P->tile_tab) RET(upload_tiles(P, &tt));
   }
@@ -537,6 +542,10 @@ extern "C" int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas
   tmp.sms = sms;
   TileTable tt;
   tt.ctas_per_sm = ctas_per_sm;
+  if (desc->reserved0 == 1) {  // the single-sweep kernel's strip geometry
+    tt.strip_out = FUSED_STRIP_OUT;
+    tt.col_shift = FUSED_COL_SHIFT;
+  }
   if (weights && n_weights > 0) tt.weight.assign(weights, weights + n_weights);
   std::vector<Tile> tiles;
   std::vector<int> cta_begin;
@@ -703,7 +712,7 @@ extern "C" int b200cg_csr_apply(b200cg_plan_t P, const double* x_host, double* y
 
 extern "C" int b200cg_cta_times(b200cg_plan_t P, int flavour, uint64_t* out, int capacity, int* n_ctas) {
   if (!P || !out || !n_ctas) return fail(B200CG_ERR_INVALID_ARG, "plan/out/n_ctas is NULL");
-  if (flavour < 0 || flavour > 2) return fail(B200CG_ERR_INVALID_ARG, "flavour %d outside [0, 2]", flavour);
+  if (flavour < 0 || flavour > 3) return fail(B200CG_ERR_INVALID_ARG, "flavour %d outside [0, 3]", flavour);
   NEED_GEOMETRY(P);
   const int n = std::min(P->clock_ctas[flavour], capacity);
   CU(cudaSetDevice(P->desc.device));

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "csr_kernels.cuh"
 #include "cluster_kernel.cuh"
+#include "fused_kernel.cuh"
 #include "comm.h"
 
 // ------------------------------------------------------------------------------------------- errors
@@ -56,11 +57,13 @@ struct GraphEntry {
   int kernels = 0;
 };
 
-struct TileTable {  // one per sweep flavour: 0 = dot phase, 1 = update without x, 2 = everything else
+struct TileTable {  // one per sweep flavour: 0 = dot phase, 1 = update without x, 2 = everything else, 3 = single sweep
   Tile* d_tiles = nullptr;
   int* d_cta_begin = nullptr;
   size_t tile_capacity = 0;
   int ctas_per_sm = 2;
+  int strip_out = STRIP_OUT;   // columns written per strip; a strip's first staged storage column is
+  int col_shift = 0;           //   strip * strip_out + col_shift  (fused_kernel.cuh: 480 / 2)
   int grid = 0, n_tiles = 0;
   bool balanced = false;       // feedback balancing applies (long marches)
   std::vector<double> weight;  // relative share of the sweep per CTA
@@ -74,11 +77,12 @@ struct b200cg_plan_s {
   b200cg_plan_desc desc;
   Geom g;
   int sms = 148;
-  TileTable tile_tab[3];  // sweep work lists per flavour
+  TileTable tile_tab[4];  // sweep work lists per flavour
   int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int shape_dot = 3, shape_upd = 2, shape_nox = 2;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   bool cluster_enabled = true;                      // small-grid path allowed (B200CG_CLUSTER=0 disables)
+  bool single_sweep_default = false;                // B200CG_SINGLE_SWEEP=1: single-sweep iteration unless a solve says no
   bool cluster16_ok = false;                        // a 16-CTA cluster of the small-grid kernel can be scheduled
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
@@ -95,8 +99,8 @@ struct b200cg_plan_s {
   CbRecord* d_log = nullptr;
   CbRecord* h_log = nullptr;  // pinned mirror
   int* h_stop = nullptr;      // mapped flag the cluster kernel polls (interrupt requests)
-  unsigned long long* d_clock[3] = {nullptr, nullptr, nullptr};  // per-CTA start/end stamps per sweep flavour
-  int clock_ctas[3] = {0, 0, 0};
+  unsigned long long* d_clock[4] = {nullptr, nullptr, nullptr, nullptr};  // per-CTA start/end stamps per sweep flavour
+  int clock_ctas[4] = {0, 0, 0, 0};
   int* d_stop = nullptr;
   double* d_partials = nullptr;
   int partial_slots = 0;

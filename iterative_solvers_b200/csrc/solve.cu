@@ -21,13 +21,14 @@ extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_hos
 }
 
 // ------------------------------------------------------------------------------------------- solve
-enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8 };
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16 };
 
 // Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
 // read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
 static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
   cudaStream_t s = P->stream;
   const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR, xdefer = variant & V_XDEFER;
+  const bool fused = variant & V_FUSED;
   int kernels = 0;
   CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200CG_OK;
@@ -57,6 +58,17 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     a.r_out = P->r[par ^ 1];
     a.p_out = P->p[par ^ 1];
     a.u = P->u;
+    if (fused) {
+      // single-sweep iteration: one kernel; x touched on odd iterations only (the event slots of the absent dot
+      // phase collapse to zero length)
+      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+      if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
+      rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+      if (k == 1) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
+      continue;
+    }
     const int fl = xdefer ? ((k & 1) ? F_X2 : F_NOX) : ((with_u ? F_U : 0) | (report ? F_REPORT : 0));
     // sharded plans: reductions and halo rows over NVLink peer memory (no NCCL call in the loop); the per-iteration
     // report variant keeps the NCCL exchange
@@ -199,7 +211,7 @@ struct SolveCall {
   void* user;
   const volatile int* stop_flag;
   bool csr, with_u, report;
-  bool xdefer = false, use_cluster = false, interrupted = false;
+  bool xdefer = false, fused = false, use_cluster = false, interrupted = false;
   unsigned int consumed = 0;  // callback records already delivered
   double dot_ms = 0.0, upd_even_ms = 0.0, upd_odd_ms = 0.0;
   int samples = 0;
@@ -345,6 +357,15 @@ static int launch_init(SolveCall& c) {
     RET(exchange_halo2(P, P->r[0], P->p[0]));
     c.info->kernel_launches += 1;
   }
+  if (c.fused) {
+    // single-sweep iteration: alpha_0 = r0.r0 / r0.A r0 needs one operator application up front; the dot sweep with
+    // beta = 0 and p_old = 0 is exactly that (p = r0)
+    TileArgs a = base_args(P);
+    a.r_in = P->r[0];
+    a.p_in = P->p[0];
+    RET((launch_tile<MODE_DOT, 0>(P, a, s)));
+    c.info->kernel_launches += 1;
+  }
   return B200CG_OK;
 }
 
@@ -376,14 +397,18 @@ static int run_graph_solve(SolveCall& c) {
   b200cg_plan_s* P = c.P;
   const b200cg_params* prm = c.prm;
   cudaStream_t s = P->stream;
+  // single-sweep iteration (opt-in): relative-residual rule without report on an unsharded plan
+  const bool want_fused = prm->single_sweep == 1 || (prm->single_sweep == 0 && P->single_sweep_default);
+  c.fused = want_fused && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2 && P->desc.world <= 1;
   RET(launch_init(c));
   int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
   if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
   K = std::max(2, (K + 1) & ~1);
   K = std::min(K, c.report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
   // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
-  c.xdefer = P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2;
-  const int variant = c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0));
+  c.xdefer = c.fused || (P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2);
+  const int variant = c.fused ? V_FUSED
+                              : (c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0)));
   GraphEntry& ge = P->graphs[variant * 4096 + K];
   if (!ge.exec) RET(build_graph(P, variant, K, &ge));
 
@@ -402,7 +427,7 @@ static int run_graph_solve(SolveCall& c) {
     if (st.done) break;
     if (P->balance_rounds > 0 && !c.csr && advanced >= 2) {
       // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
-      for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
+      for (int fl = 0; fl < 4; ++fl) RET(rebalance_tiles(P, fl));
       --P->balance_rounds;
     }
     if (c.stop_flag && *c.stop_flag) {
@@ -463,6 +488,7 @@ static void fill_info(const SolveCall& c, const DevState& st) {
   info->upd_odd_ms = c.samples ? c.upd_odd_ms / c.samples : 0.0;
   info->kernel_samples = c.samples;
   info->x_deferral = c.xdefer ? 1 : 0;
+  info->single_sweep = c.fused ? 1 : 0;
   info->cluster_path = c.use_cluster ? 1 : 0;
   info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !c.report && !c.use_cluster) ? 1 : 0;
 }

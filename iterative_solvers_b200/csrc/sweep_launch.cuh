@@ -75,6 +75,29 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
   return launch_shape<MODE, FLAGS, 0>(P, a, s);
 }
 
+// The single-sweep iteration (fused_kernel.cuh): 4-row stages, 2 CTAs/SM, ~96 KB of copy destinations per CTA.
+template <int FLAGS>
+static int launch_fused(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
+  constexpr int HS = 4, NST = FusedCfg<FLAGS>::X2 ? 2 : 3, CTAS = 2;
+  auto kernel = cg_fused_kernel<FLAGS, HS, NST, CTAS>;
+  constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST>();
+  static thread_local bool configured[64] = {};
+  const int dev = P->desc.device & 63;
+  if (!configured[dev]) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  const TileTable& tt = P->tile_tab[3];
+  if (tt.n_tiles <= 0) return B200CG_OK;
+  a.tiles = tt.d_tiles;
+  a.cta_begin = tt.d_cta_begin;
+  a.cta_clock = P->d_clock[3];
+  P->clock_ctas[3] = tt.grid;
+  kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
+  CU(cudaGetLastError());
+  return B200CG_OK;
+}
+
 static TileArgs base_args(b200cg_plan_s* P) {
   TileArgs a;
   memset(&a, 0, sizeof(a));

@@ -1,0 +1,118 @@
+"""GPU parity of the opt-in single-sweep iteration (b200cg_params.single_sweep = 1, csrc/fused_kernel.cuh).
+
+One kernel per iteration; alpha comes from the single-reduction CG recurrence instead of p.Ap. The bar is the same as
+for the default path (BASELINE.json north_star): iteration count within +-1 of the reference, solution within 1e-10
+relative. scripts/study_single_reduction_cg.py (numpy) and scripts/model_single_sweep.py (lane-level model of the
+kernel's data flow) are the CPU-side evidence; these tests are the product check through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+DOMAINS = {0: (0.0, 1.0), 1: (1.0, 2.0)}
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from iterative_solvers_b200 import capi as c
+
+    c.lib()
+    assert c.device_count() >= 1, "these tests need a CUDA device"
+    return c
+
+
+def relmax(x, ref):
+    return np.max(np.abs(x - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+def fused_solve(p, **kw):
+    # small_grid_path=1: small grids would otherwise take the cluster-resident kernel
+    x, info = p.solve(single_sweep=1, small_grid_path=1, **kw)
+    assert info["single_sweep"] == 1 and info["cluster_path"] == 0
+    return x, info
+
+
+@pytest.mark.parametrize("n,a_tag,iters", [(6, 1, 13), (30, 1, 88), (64, 0, 178), (128, 0, 352), (128, 1, 362)])
+def test_reference_fixtures(capi, golden_ref, n, a_tag, iters):
+    """The grids the unmodified reference was run on (tests/golden): same iteration counts, same solution."""
+    tag = f"mf_n{n}_a{a_tag}"
+    a, b = DOMAINS[a_tag]
+    with capi.Plan(n, n, a, b, a, b) as p:
+        x, info = fused_solve(p, b=golden_ref[tag + "_rhs"], eps_rel=1e-8, max_it=10000)
+        assert abs(info["iterations"] - iters) <= 1
+        assert info["converged"]
+        assert relmax(x, golden_ref[tag + "_x"]) < REL
+        assert info["r_l2"] <= 1e-8 * info["r0_l2"]
+
+
+@pytest.mark.parametrize("n,domain,tile_rows,eps", [(256, 0, 0, 1e-8), (600, 0, 0, 1e-6), (1030, 0, 7, 1e-5),
+                                                     (333, 1, 0, 1e-8), (1009, 1, 5, 1e-5), (64, 0, 1, 1e-9),
+                                                     (64, 0, 3, 1e-9)])
+def test_strips_tiles_and_domains_vs_oracle(capi, oracle_mod, n, domain, tile_rows, eps):
+    """Several strips (n > 480), ragged and one-row tiles, the full rectangle."""
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
+    ref = o.mf_solve(eps=eps, max_it=20000)
+    with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, tile_rows=tile_rows) as p:
+        x, info = fused_solve(p, b=o.rhs(), eps_rel=eps, max_it=20000)
+        assert abs(info["iterations"] - ref["iterations"]) <= 1
+        assert relmax(x, ref["x"]) < REL
+
+
+@pytest.mark.parametrize("n,m", [(7, 7), (9, 12), (33, 20), (1201, 777)])
+def test_general_lshape(capi, oracle_mod, n, m):
+    o = oracle_mod.Oracle(m, n, 0.0, 1.0, 0.0, 1.0, oracle_mod.LSHAPE_ANY)
+    ref = o.mf_solve(eps=1e-7, max_it=20000)
+    with capi.Plan(m, n, 0.0, 1.0, 0.0, 1.0, domain=capi.DOMAIN_LSHAPE_ANY) as p:
+        x, info = fused_solve(p, b=o.rhs(), eps_rel=1e-7, max_it=20000)
+        assert abs(info["iterations"] - ref["iterations"]) <= 1
+        assert relmax(x, ref["x"]) < REL
+
+
+def test_fixed_iteration_counts_match_the_default_path(capi, oracle_mod):
+    """Stopped early at odd and even counts (the pending x update of an even last sweep is flushed): iterate by iterate
+    the single-sweep path stays at rounding distance from the two-sweep path and from the oracle."""
+    n = 512
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, 0)
+    b = o.rhs()
+    with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0) as p:
+        for iters in (1, 2, 7, 40):
+            ref = o.mf_solve(b=b, eps=0.0, max_it=iters)
+            xd, idf = p.solve(b=b, eps_rel=0.0, max_it=iters, single_sweep=2)
+            xs, isf = fused_solve(p, b=b, eps_rel=0.0, max_it=iters, iters_per_graph=6)
+            assert idf["single_sweep"] == 0
+            assert isf["iterations"] == idf["iterations"] == iters
+            assert relmax(xs, ref["x"]) < 1e-12 and relmax(xs, xd) < 1e-12
+            assert abs(isf["r_l2"] - idf["r_l2"]) <= 1e-11 * idf["r_l2"]
+
+
+def test_edge_cases_and_fallbacks(capi, oracle_mod):
+    o = oracle_mod.Oracle(64, 64, 0.0, 1.0, 0.0, 1.0, 0)
+    b, u = o.rhs(), o.true_solution()
+    with capi.Plan(64, 64, 0.0, 1.0, 0.0, 1.0) as p:
+        x, info = fused_solve(p, b=np.zeros_like(b), eps_rel=1e-8, max_it=100)  # zero rhs: nothing to do
+        assert info["iterations"] == 0 and not np.any(x)
+        x, info = fused_solve(p, b=b, eps_rel=1e-8, max_it=0)
+        assert info["iterations"] == 0 and not info["converged"]
+        # where the single sweep does not apply the request is ignored and the usual path runs
+        ref = o.msg_solve(b=b, u=u, eps_p=1e-8, eps_r=1e-8, max_it=20000)
+        x, info = p.solve(b=b, u=u, rule=capi.RULE_MAXNORM, eps_p=1e-8, eps_r=1e-8, max_it=20000, single_sweep=1,
+                          small_grid_path=1)
+        assert info["single_sweep"] == 0 and info["iterations"] == ref["iterations"]
+        got = []
+        x, info = p.solve(b=b, u=u, eps_rel=1e-8, max_it=20000, single_sweep=1, small_grid_path=1,
+                          callback=lambda it, pr, r, e: got.append(it))
+        assert info["single_sweep"] == 0 and len(got) > 0
+
+
+def test_large_grid_property(capi):
+    """4096^2 (config 2 size): 60 single-sweep iterations against 60 two-sweep iterations on the device-built rhs."""
+    n = 4096
+    with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0) as p:
+        p.build_rhs()
+        xd, idf = p.solve(rhs_on_device=True, eps_rel=0.0, max_it=60, single_sweep=2)
+        xs, isf = p.solve(rhs_on_device=True, eps_rel=0.0, max_it=60, single_sweep=1)
+        assert isf["single_sweep"] == 1 and idf["single_sweep"] == 0
+        assert isf["iterations"] == idf["iterations"] == 60
+        assert relmax(xs, xd) < 1e-11
+        assert abs(isf["r_l2"] - idf["r_l2"]) <= 1e-10 * idf["r_l2"]

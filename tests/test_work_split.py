@@ -20,22 +20,25 @@ def unknown_mask(n, m, domain):
     return mask
 
 
-def coverage(n, m, tiles):
+FUSED_STRIP_OUT, FUSED_SHIFT = 480, 2  # csrc/fused_kernel.cuh
+
+
+def coverage(n, m, tiles, strip_out=STRIP_OUT, shift=0):
     cov = np.zeros((m + 1, n + 1), dtype=np.int32)
     for col0, ya, yb, xlo in tiles:
-        x0, x1 = max(col0, xlo), min(col0 + STRIP_OUT - 1, n - 1)
-        assert col0 % STRIP_OUT == 0 and ya < yb
+        x0, x1 = max(col0 - shift, xlo), min(col0 - shift + strip_out - 1, n - 1)
+        assert (col0 - shift) % strip_out == 0 and ya < yb
         if x0 <= x1:
             cov[ya:yb, x0:x1 + 1] += 1
     return cov
 
 
-def check_split(n, m, domain, world, sms, ctas, weights=None, tile_rows=0):
+def check_split(n, m, domain, world, sms, ctas, weights=None, tile_rows=0, fused=False):
     total = np.zeros((m + 1, n + 1), dtype=np.int32)
     for rank in range(world):
         ylo, yhi, lo, hi, N = capi.partition(m, n, domain=domain, rank=rank, world=world)
         tiles, cta_begin = capi.work_split(m, n, domain=domain, rank=rank, world=world, sms=sms, ctas_per_sm=ctas,
-                                           weights=weights, tile_rows=tile_rows)
+                                           weights=weights, tile_rows=tile_rows, fused=fused)
         grid = len(cta_begin) - 1
         assert 1 <= grid <= sms * ctas
         assert cta_begin[0] == 0 and cta_begin[-1] == len(tiles) and np.all(np.diff(cta_begin) >= 0)
@@ -45,7 +48,7 @@ def check_split(n, m, domain, world, sms, ctas, weights=None, tile_rows=0):
             assert np.all(lower | (tiles[:, 1] > m // 2))
             assert np.all(tiles[lower & (tiles[:, 1] <= m // 2), 3] == n // 2 + 1)
             assert np.all(tiles[tiles[:, 1] > m // 2, 3] == 1)
-        cov = coverage(n, m, tiles)
+        cov = coverage(n, m, tiles, FUSED_STRIP_OUT, FUSED_SHIFT) if fused else coverage(n, m, tiles)
         assert cov.sum() == hi - lo
         total += cov
     assert np.array_equal(total, unknown_mask(n, m, domain))
@@ -104,3 +107,11 @@ def test_small_machines_and_errors():
         capi.work_split(128, 128, sms=0)
     with pytest.raises(capi.B200CGError):
         capi.work_split(129, 129)  # odd n: not a reference grid
+
+
+@pytest.mark.parametrize("n", [6, 30, 478, 480, 482, 962, 2048])
+def test_single_sweep_strip_geometry(n):
+    """The single-sweep kernel cuts strips of 480 written columns (desc.reserved0 = 1)."""
+    check_split(n, n, capi.DOMAIN_LSHAPE, 1, 148, 2, fused=True)
+    check_split(n, n + 3, capi.DOMAIN_RECT, 1, 148, 2, fused=True, tile_rows=3)
+    check_split(n + 1, n, capi.DOMAIN_LSHAPE_ANY, 1, 4, 2, fused=True)
