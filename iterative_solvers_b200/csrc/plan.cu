@@ -434,6 +434,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
+    P->balance_rounds_fused = P->balance_rounds;
     P->cluster_enabled = env_int("B200CG_CLUSTER", 1) != 0;
     P->single_sweep_default = env_int("B200CG_SINGLE_SWEEP", 0) != 0;
     if (!P->generic && P->cluster_enabled) {

@@ -425,10 +425,16 @@ static int run_graph_solve(SolveCall& c) {
     sample_kernel_times(c, advanced);
     deliver_callbacks(c);
     if (st.done) break;
-    if (P->balance_rounds > 0 && !c.csr && advanced >= 2) {
-      // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here)
-      for (int fl = 0; fl < 4; ++fl) RET(rebalance_tiles(P, fl));
-      --P->balance_rounds;
+    int& rounds = c.fused ? P->balance_rounds_fused : P->balance_rounds;
+    if (rounds > 0 && !c.csr && advanced >= 2) {
+      // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here); only
+      // the flavours this loop launches carry fresh stamps
+      if (c.fused) {
+        RET(rebalance_tiles(P, 3));
+      } else {
+        for (int fl = 0; fl < 3; ++fl) RET(rebalance_tiles(P, fl));
+      }
+      --rounds;
     }
     if (c.stop_flag && *c.stop_flag) {
       c.interrupted = true;
