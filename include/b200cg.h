@@ -107,7 +107,7 @@ typedef struct {
                               (40 instead of 56 bytes per unknown) by forming alpha from the single-reduction CG
                               recurrence (Chronopoulos-Gear) instead of p.Ap - the same iterates in exact arithmetic,
                               <= 4e-14 relative apart in fp64 on the reference's grids
-                              (scripts/study_single_reduction_cg.py). 0 = the plan's default (off unless
+                              (tests/studies/single_reduction_cg.py). 0 = the plan's default (off unless
                               B200CG_SINGLE_SWEEP=1), 2 = never. Ignored where it does not apply */
   int reserved[5];
 } b200cg_params;

@@ -10,7 +10,7 @@
 // A r' needs r' at the four neighbours, i.e. A p one node further out, i.e. p two nodes out: the sweep carries a halo
 // of two rows / two columns and recomputes p and r' there. Element-wise arithmetic is unchanged (separately rounded
 // multiply/add in the reference's order, matrix_free_system.cpp:216-266, :422-438); only the way alpha is formed
-// differs, and scripts/study_single_reduction_cg.py shows the iterates stay within 4e-14 of the reference's on every
+// differs, and tests/studies/single_reduction_cg.py shows the iterates stay within 4e-14 of the reference's on every
 // golden grid (same iteration counts). Opt-in (b200cg_params.single_sweep / B200CG_SINGLE_SWEEP), REL_L2 rule,
 // unsharded plans.
 //

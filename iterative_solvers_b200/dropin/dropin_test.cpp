@@ -2,6 +2,7 @@
 // (qt_gui/src/mainwindow.cpp:185-266,290-308; solver/main.cpp:596-712) and dumps the results for pytest
 // (tests/test_dropin_gpu.py) to compare with the golden fixtures. Usage: dropin_test <command> <args...> <outdir>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -174,6 +175,78 @@ int cmd_errors(char**) {
   return caught == 3 ? 0 : 1;
 }
 
+int cmd_io(char**) {
+  // ResultsIO without a device: save / load round trip of an L-shaped result (section lengths != n*m), a file without
+  // the optional coordinate sections (dirichlet_solver.cpp:388-402), a truncated file, the gnuplot surface format
+  SolverResults r;
+  const int n = 6, m = 6, count = 16;  // 16 unknowns on the 6x6 L-shaped grid
+  for (int i = 0; i < count; ++i) {
+    r.solution.push_back(1.0 + 0.125 * i);
+    r.true_solution.push_back(1.0 + 0.125 * i + 1e-7);
+    r.residual.push_back((i % 2 ? -1.0 : 1.0) * 3.5e-9 * (i + 1));
+    r.error.push_back(-1e-7);
+    r.x_coords.push_back(0.5 + i / 12.0);
+    r.y_coords.push_back(1.0 / 6.0 * (1 + i / 4));
+  }
+  r.residual_norm = 5.6e-8;
+  r.error_norm = 1e-7;
+  r.iterations = 13;
+  r.converged = true;
+  r.stop_reason = "Converged by residual";
+  const std::string path = g_out + "/roundtrip.txt";
+  int failures = 0;
+  failures += ResultsIO::saveResults(path, r, n, m, 0.0, 1.0, 2.0, 3.0, "MSG Solver") ? 0 : 1;
+  SolverResults back;
+  int n2 = 0, m2 = 0;
+  double p[4] = {0, 0, 0, 0};
+  std::string name;
+  failures += ResultsIO::loadResults(path, back, n2, m2, p[0], p[1], p[2], p[3], name) ? 0 : 1;
+  auto close = [](const std::vector<double>& x, const std::vector<double>& y) {
+    if (x.size() != y.size()) return false;
+    for (size_t i = 0; i < x.size(); ++i)
+      if (std::abs(x[i] - y[i]) > 1e-6 * std::abs(y[i])) return false;  // the text format keeps 7 digits
+    return true;
+  };
+  failures += (n2 == n && m2 == m && p[0] == 0.0 && p[1] == 1.0 && p[2] == 2.0 && p[3] == 3.0) ? 0 : 1;
+  failures += (name == "MSG Solver" && back.stop_reason == r.stop_reason && back.iterations == 13 && back.converged) ? 0 : 1;
+  failures += (close(back.solution, r.solution) && close(back.true_solution, r.true_solution) &&
+               close(back.residual, r.residual) && close(back.error, r.error) && close(back.x_coords, r.x_coords) &&
+               close(back.y_coords, r.y_coords)) ? 0 : 1;
+  failures += (std::abs(back.residual_norm - r.residual_norm) <= 1e-6 * r.residual_norm) ? 0 : 1;
+
+  // a file written by an older writer: no coordinate sections
+  {
+    std::ifstream in(path);
+    std::ofstream out(g_out + "/no_coords.txt");
+    std::string line;
+    while (std::getline(in, line)) {
+      if (line == "X_COORDS") break;
+      out << line << "\n";
+    }
+  }
+  SolverResults short_back;
+  failures += ResultsIO::loadResults(g_out + "/no_coords.txt", short_back, n2, m2, p[0], p[1], p[2], p[3], name) ? 0 : 1;
+  failures += (short_back.solution.size() == (size_t)count && short_back.error.size() == (size_t)count &&
+               short_back.x_coords.empty() && short_back.y_coords.empty()) ? 0 : 1;
+
+  // broken inputs are refused, not half-read
+  {
+    std::ofstream(g_out + "/truncated.txt") << "PARAMETERS\n6 6\n0 1 2 3\nMSG Solver\nCONVERGENCE\n13\n1\nok\n1e-8 1e-7\nSOLUTION\n1.0\n";
+    std::ofstream(g_out + "/garbage.txt") << "hello\n";
+  }
+  SolverResults bad;
+  failures += ResultsIO::loadResults(g_out + "/truncated.txt", bad, n2, m2, p[0], p[1], p[2], p[3], name) ? 1 : 0;
+  failures += ResultsIO::loadResults(g_out + "/garbage.txt", bad, n2, m2, p[0], p[1], p[2], p[3], name) ? 1 : 0;
+  failures += ResultsIO::loadResults(g_out + "/does_not_exist.txt", bad, n2, m2, p[0], p[1], p[2], p[3], name) ? 1 : 0;
+
+  // gnuplot surface: "x y z" per node, blank line between grid rows, interior nodes of [0,1]x[2,3]
+  std::vector<std::vector<double>> grid = {{1.0, 2.0, 3.0}, {4.0, 5.0, 6.0}};
+  failures += ResultsIO::saveSolutionFor3D(g_out + "/surface.txt", grid, 0.0, 1.0, 2.0, 3.0) ? 0 : 1;
+  failures += ResultsIO::saveSolutionFor3D(g_out + "/empty.txt", {}, 0.0, 1.0, 2.0, 3.0) ? 1 : 0;
+  std::ofstream(g_out + "/info.txt") << "failures=" << failures << "\n";
+  return failures == 0 ? 0 : 1;
+}
+
 int cmd_stop(char** a) {
   // requestStop() from another thread while solve() runs on this one (mainwindow.cpp:268-288)
   const int n = std::atoi(a[0]);
@@ -196,7 +269,7 @@ int cmd_stop(char** a) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|grid|errors|stop> <args...> <outdir>\n");
+    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|grid|errors|io|stop> <args...> <outdir>\n");
     return 2;
   }
   g_out = argv[argc - 1];
@@ -206,6 +279,7 @@ int main(int argc, char** argv) {
     if (cmd == "mf" && argc == 9) return cmd_mf(argv + 2);
     if (cmd == "grid" && argc == 10) return cmd_grid(argv + 2);
     if (cmd == "errors") return cmd_errors(argv + 2);
+    if (cmd == "io" && argc == 3) return cmd_io(argv + 2);
     if (cmd == "stop" && argc == 4) return cmd_stop(argv + 2);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "dropin_test: %s\n", e.what());

@@ -2,7 +2,7 @@
 parity bar (iterations +-1, x within 1e-10 relative) of the reference's CG on the reference grids?"""
 import sys, time
 import numpy as np
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle as om
 
 def make_apply(o, n, m):
@@ -65,16 +65,23 @@ def cg_single(b, apply, eps, max_it):
         gamma = gamma_new
     return x, it
 
-for n, eps in [(64, 1e-8), (128, 1e-8), (256, 1e-8), (512, 1e-8), (1100, 1e-6), (1024, 1e-8)]:
+def compare(n, eps):
+    """(oracle iterations, single-reduction iterations, relative max difference of x) on the n x n L-shaped grid."""
     o = om.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, om.LSHAPE)
     A, xk, yk, mask = make_apply(o, n, n)
     b = to_grid(o, o.rhs(), mask)
     ap = lambda p: apply_grid(p, A, xk, yk, mask)
-    t = time.time()
     ref = o.mf_solve(b=o.rhs(), eps=eps, max_it=50000)
     xr, itr = cg_ref(b, ap, eps, 50000)
     xs, its = cg_single(b, ap, eps, 50000)
     xo = to_grid(o, ref["x"], mask)
     sc = np.max(np.abs(xo))
-    print(f"n={n}: oracle it {ref['iterations']}, numpy-CG it {itr} (diff {np.max(np.abs(xr-xo))/sc:.2e}), "
-          f"single-reduction it {its} (diff vs oracle {np.max(np.abs(xs-xo))/sc:.2e}) [{time.time()-t:.1f}s]", flush=True)
+    return ref["iterations"], itr, its, np.max(np.abs(xr - xo)) / sc, np.max(np.abs(xs - xo)) / sc
+
+
+if __name__ == "__main__":
+    for n, eps in [(64, 1e-8), (128, 1e-8), (256, 1e-8), (512, 1e-8), (1100, 1e-6), (1024, 1e-8)]:
+        t = time.time()
+        it_o, it_r, it_s, d_r, d_s = compare(n, eps)
+        print(f"n={n}: oracle it {it_o}, numpy-CG it {it_r} (diff {d_r:.2e}), "
+              f"single-reduction it {it_s} (diff vs oracle {d_s:.2e}) [{time.time()-t:.1f}s]", flush=True)

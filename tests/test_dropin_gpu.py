@@ -57,6 +57,23 @@ def test_cpp_surface_fails_loudly_without_a_gpu(driver, tmp_path):
     assert "no" in proc.stderr.lower() and "device" in proc.stderr.lower()
 
 
+def test_results_io_formats_on_the_host(driver, tmp_path):
+    """ResultsIO (dirichlet_solver.cpp:330-470) needs no device: save/load round trip with L-shape section lengths,
+    files without the optional coordinate sections, refused broken files, the gnuplot surface layout."""
+    run(driver, "io", tmp_path)
+    assert info(tmp_path)["failures"] == "0"
+    text = open(os.path.join(tmp_path, "roundtrip.txt"), encoding="utf-8").read().split("\n")
+    assert text[0] == "PARAMETERS" and text[1] == "6 6" and text[3] == "MSG Solver" and text[4] == "CONVERGENCE"
+    for title in ("SOLUTION", "TRUE_SOLUTION", "RESIDUAL", "ERROR", "X_COORDS", "Y_COORDS"):
+        i = text.index(title)
+        float(text[i + 1]) and float(text[i + 16])  # 16 values per section, one per line
+    blocks = open(os.path.join(tmp_path, "surface.txt"), encoding="utf-8").read().strip().split("\n\n")
+    rows = [np.array([[float(v) for v in line.split()] for line in b.strip().split("\n")]) for b in blocks]
+    assert len(rows) == 2 and all(r.shape == (3, 3) for r in rows)
+    assert np.allclose(rows[0][:, 0], [0.25, 0.5, 0.75]) and np.allclose(rows[0][:, 1], 2 + 1 / 3)
+    assert np.allclose(rows[1][:, 1], 2 + 2 / 3) and np.array_equal(rows[1][:, 2], [4.0, 5.0, 6.0])
+
+
 # ---------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_dirichlet_solver_gui_defaults(driver, tmp_path, golden_ref):

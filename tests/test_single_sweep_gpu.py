@@ -2,7 +2,7 @@
 
 One kernel per iteration; alpha comes from the single-reduction CG recurrence instead of p.Ap. The bar is the same as
 for the default path (BASELINE.json north_star): iteration count within +-1 of the reference, solution within 1e-10
-relative. scripts/study_single_reduction_cg.py (numpy) and scripts/model_single_sweep.py (lane-level model of the
+relative. tests/studies/single_reduction_cg.py (numpy) and scripts/model_single_sweep.py (lane-level model of the
 kernel's data flow) are the CPU-side evidence; these tests are the product check through the C ABI."""
 import numpy as np
 import pytest
