@@ -34,6 +34,12 @@ struct FusedCfg {
   static constexpr bool X2 = (FLAGS & F_X2) != 0;   // odd iteration: x += alpha_prev * p_old + alpha * p
   static constexpr bool NOX = !X2;                  // even iteration: x untouched, its update stays pending
   static constexpr int NSTREAM = X2 ? 3 : 2;        // p, r, [x]
+  // F_EDGE (tuning variant, B200CG_FUSED_DELTA=1): A is symmetric with a constant diagonal, so
+  //   r'.A r' = A_diag * sum r'^2 + 2 xk * sum_{horizontal edges} r'_i r'_j + 2 yk * sum_{vertical edges} r'_i r'_j ;
+  // every node owns the edge to its right and the edge above it. No second stencil, one halo row less below.
+  static constexpr bool EDGE = (FLAGS & F_EDGE) != 0;
+  static constexpr int NS = EDGE ? 3 : 2;           // gamma', delta'  |  gamma', horizontal, vertical edge sums
+  static constexpr int ROWS_BELOW = EDGE ? 1 : 2;   // rows streamed below a tile's first emit row
 };
 
 template <int FLAGS, int HS, int NST>
@@ -70,8 +76,8 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
 template <int FLAGS, int HS, int NST, int CTAS>
 __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const TileArgs a) {
   using Cfg = FusedCfg<FLAGS>;
-  constexpr bool X2 = Cfg::X2;
-  constexpr int NSTREAM = Cfg::NSTREAM;
+  constexpr bool X2 = Cfg::X2, EDGE = Cfg::EDGE;
+  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
   constexpr int STAGE_DOUBLES = HS * NSTREAM * STRIP_LOAD;
   constexpr int OFF_P = 0, OFF_R = HS * STRIP_LOAD, OFF_X = 2 * HS * STRIP_LOAD;
 
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE_DOUBLES * 8);
   uint64_t* empty = full + NST;
   StageMeta* meta = reinterpret_cast<StageMeta*>(empty + NST);
-  __shared__ double scratch[2 * 32];
+  __shared__ double scratch[NS * 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
   }
   __syncthreads();
 
-  double acc_s[2] = {0.0, 0.0};  // gamma', delta'
+  double acc_s[NS] = {0.0};  // gamma', delta'  (F_EDGE: gamma', horizontal and vertical edge sums)
   double acc_m[1] = {0.0};
   const int y_store_lo = g.ybase, y_store_hi = g.ybase + g.yrows;  // stored rows [lo, hi)
 
@@ -112,11 +118,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
         const Tile tl = a.tiles[t];
         const int col0 = tl.col0, ya = tl.ya, yb = tl.yb;
         const uint32_t row_bytes = (uint32_t)min(FUSED_STRIP_COLS, g.pitch - col0) * 8u;
-        const int S = yb - ya + 4;  // rows ya-2 .. yb+1
+        const int S = yb - ya + 2 + LO;  // rows ya-2 .. yb+1 (F_EDGE: ya-1 .. yb+1)
         for (int s0 = 0; s0 < S; s0 += HS) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const int nrows = min(HS, S - s0);
-          const int y0 = ya - 2 + s0;
+          const int y0 = ya - LO + s0;
           StageMeta m;
           m.col0 = col0; m.y0 = y0; m.nrows = nrows; m.flags = (s0 == 0) ? META_TILE_FIRST : 0;
           m.ya = ya; m.yb = yb; m.xlo = tl.xlo; m.pad = 0;
@@ -259,20 +265,33 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
           acc_s[0] = fma(R0.x, R0.x, acc_s[0]);
           acc_s[0] = fma(R0.y, R0.y, acc_s[0]);
         }
-        const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
         const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
-
-        // ---- row y-2: A r' and delta' += r'.A r'
-        if ((FULL || ((y - 2 >= ya) && (y - 2 < yb))) && writer) {
-          const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
-          const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
-          acc_s[1] = fma(R1.x, w0, acc_s[1]);
-          acc_s[1] = fma(R1.y, w1, acc_s[1]);
+        const bool emit2 = FULL || ((y - 2 >= ya) && (y - 2 < yb));
+        if (EDGE) {
+          // edges owned by the nodes of row y-1 (to the right) and of row y-2 (upwards, to row y-1)
+          if (emit1 && writer) {
+            acc_s[1] = fma(R0.x, R0.y, acc_s[1]);
+            acc_s[1] = fma(R0.y, RR0, acc_s[1]);
+          }
+          if (emit2 && writer) {
+            acc_s[NS - 1] = fma(R1.x, R0.x, acc_s[NS - 1]);
+            acc_s[NS - 1] = fma(R1.y, R0.y, acc_s[NS - 1]);
+          }
+          R1 = R0;
+        } else {
+          const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
+          // ---- row y-2: A r' and delta' += r'.A r'
+          if (emit2 && writer) {
+            const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
+            const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
+            acc_s[1] = fma(R1.x, w0, acc_s[1]);
+            acc_s[1] = fma(R1.y, w1, acc_s[1]);
+          }
+          R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
         }
 
         // ---- shift the pipeline
         P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
-        R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
         r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
         k1a = k0a;  k1b = k0b;
       };
@@ -290,8 +309,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
   }
 
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
-  if (!grid_reduce<2, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
-  finalize_fused(st, acc_s[0], acc_s[1], FLAGS);
+  if (!grid_reduce<NS, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
+  const double delta = EDGE ? g.A * acc_s[0] + 2.0 * g.xk * acc_s[1] + 2.0 * g.yk * acc_s[NS - 1] : acc_s[1];
+  finalize_fused(st, acc_s[0], delta, FLAGS);
 }
 
 }  // namespace b200cg

@@ -23,7 +23,8 @@ enum {
   F_REPORT = 2,  // UPD: reduce |dx|_2, |x-u|_2.  APPLY: reduce |b - A v|_2, append the callback record, no store
   F_SUB_B = 4,   // APPLY: out = A v - b
   F_NOX = 8,     // UPD, x-deferral: even iteration, x is not touched (its update stays pending)
-  F_X2 = 16      // UPD, x-deferral: odd iteration, applies the pending update and this one
+  F_X2 = 16,     // UPD, x-deferral: odd iteration, applies the pending update and this one
+  F_EDGE = 32    // single-sweep kernel: r'.A r' from edge sums instead of a second stencil (fused_kernel.cuh)
 };
 
 struct TileArgs {

@@ -432,6 +432,8 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_dot = env_int("B200CG_SHAPE_DOT", P->shape_dot);
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
+    P->shape_fused = env_int("B200CG_SHAPE_FUSED", P->shape_fused);
+    P->fused_edge_sums = env_int("B200CG_FUSED_DELTA", 0) != 0;
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->balance_rounds_fused = P->balance_rounds;

@@ -75,10 +75,13 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
   return launch_shape<MODE, FLAGS, 0>(P, a, s);
 }
 
-// The single-sweep iteration (fused_kernel.cuh): 4-row stages, 2 CTAs/SM, ~96 KB of copy destinations per CTA.
-template <int FLAGS>
-static int launch_fused(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
-  constexpr int HS = 4, NST = FusedCfg<FLAGS>::X2 ? 2 : 3, CTAS = 2;
+// The single-sweep iteration (fused_kernel.cuh), 2 CTAs/SM, ~96-108 KB of copy destinations per CTA.
+// Shape 0 (default): 4-row stages. Shape 1 (B200CG_SHAPE_FUSED=1, tuning knob): 3-row stages - the two register
+// pipelines of the row loop have period 3, so an unrolled 3-row stage needs no register rotation.
+template <int FLAGS, int SHAPE>
+static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
+  constexpr bool X2 = FusedCfg<FLAGS>::X2;
+  constexpr int HS = SHAPE == 1 ? 3 : 4, NST = SHAPE == 1 ? (X2 ? 3 : 4) : (X2 ? 2 : 3), CTAS = 2;
   auto kernel = cg_fused_kernel<FLAGS, HS, NST, CTAS>;
   constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST>();
   static thread_local bool configured[64] = {};
@@ -96,6 +99,12 @@ static int launch_fused(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
+}
+template <int FLAGS>
+static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  if (P->fused_edge_sums)  // B200CG_FUSED_DELTA=1 (tuning variant): r'.A r' from edge sums
+    return P->shape_fused == 1 ? launch_fused_shape<FLAGS | F_EDGE, 1>(P, a, s) : launch_fused_shape<FLAGS | F_EDGE, 0>(P, a, s);
+  return P->shape_fused == 1 ? launch_fused_shape<FLAGS, 1>(P, a, s) : launch_fused_shape<FLAGS, 0>(P, a, s);
 }
 
 static TileArgs base_args(b200cg_plan_s* P) {

@@ -119,3 +119,30 @@ def test_large_grid_property(capi):
         assert isf["iterations"] == idf["iterations"] == 60
         assert relmax(xs, xd) < 1e-11
         assert abs(isf["r_l2"] - idf["r_l2"]) <= 1e-10 * idf["r_l2"]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200CG_TEST_EXPERIMENTAL") != "1",
+                    reason="tuning variants of the single-sweep kernel that have only been checked by the CPU model "
+                           "(scripts/model_single_sweep.py); set B200CG_TEST_EXPERIMENTAL=1 to run them")
+@pytest.mark.parametrize("env", [{"B200CG_FUSED_DELTA": "1"}, {"B200CG_SHAPE_FUSED": "1"},
+                                 {"B200CG_FUSED_DELTA": "1", "B200CG_SHAPE_FUSED": "1"}])
+def test_experimental_variants(capi, oracle_mod, env):
+    """r'.A r' from edge sums (no second stencil) and 3-row stages: same bar as the default single-sweep kernel."""
+    import os
+
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        for n, domain, tile_rows, eps in [(64, 0, 0, 1e-8), (64, 0, 3, 1e-8), (600, 0, 0, 1e-6), (333, 1, 5, 1e-8)]:
+            o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
+            ref = o.mf_solve(eps=eps, max_it=20000)
+            with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, tile_rows=tile_rows) as p:  # knobs read here
+                x, info = fused_solve(p, b=o.rhs(), eps_rel=eps, max_it=20000)
+                assert abs(info["iterations"] - ref["iterations"]) <= 1
+                assert relmax(x, ref["x"]) < REL
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
