@@ -1,0 +1,27 @@
+"""The lane-level CPU model of the single-sweep kernel's data flow (scripts/model_single_sweep.py) on the real tile
+tables of b200cg_work_split: strips of 480 written columns, 64-column warp windows, the two-deep row pipeline, per-row
+masks across the two blocks of the L, stale shared-memory columns as NaN. It pins the index arithmetic the CUDA kernel
+(csrc/fused_kernel.cuh) implements, for both ways of forming r'.A r'. No GPU needed."""
+import importlib.util
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def model():
+    spec = importlib.util.spec_from_file_location("model_single_sweep", os.path.join(ROOT, "scripts", "model_single_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("edge", [False, True], ids=["stencil", "edge-sums"])
+@pytest.mark.parametrize("n,m,lshape,iters,tile_rows", [(30, 30, True, 5, 0), (64, 64, True, 4, 5), (70, 46, True, 4, 0),
+                                                        (77, 33, False, 4, 3), (500, 24, True, 3, 0)])
+def test_model_matches_plain_single_reduction_cg(model, n, m, lshape, iters, tile_rows, edge):
+    worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows, edge=edge)
+    assert ntiles >= 1
+    assert worst < 1e-9 and dx < 1e-10 and dr < 1e-10
