@@ -35,9 +35,9 @@ struct Geom {
 };
 
 // One unit of sweep work: rows [ya, yb) of one 512-column strip. The host cuts the sweep into equal-work tiles
-// and deals them to the resident CTAs (b200cg.cu: build_tiles); the producer warp just walks its list.
+// and deals them to the resident CTAs (plan.cu: build_tiles); the producer warp just walks its list.
 struct Tile {
-  int col0;  // storage column of the first loaded column (strip * STRIP_OUT)
+  int col0;  // storage column of the first loaded column (strip * STRIP_OUT; single-sweep kernel: strip * 480 + 2)
   int ya, yb;
   int xlo;   // first unknown x in these rows (1, or xsplit+1 in block B)
 };

@@ -58,13 +58,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ double2 ld_ro2(const double* p, bool ok) {
-  // read-only for the lifetime of the kernel: non-coherent path
-  return ok ? __ldg(reinterpret_cast<const double2*>(p)) : make_double2(0.0, 0.0);
-}
-__device__ __forceinline__ double2 ld_rw2(const double* p, bool ok) {
-  return ok ? *reinterpret_cast<const double2*>(p) : make_double2(0.0, 0.0);
-}
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 // sweep outputs: written once, next read a whole sweep (GBs) later
 __device__ __forceinline__ void st2_out(double* p, double2 v) {
