@@ -7,7 +7,11 @@ Dirichlet system on an n x n grid through the C ABI (b200cg_solve), i.e. what Ma
           there; timed on the device (CUDA events of the library's solve stream), max over ranks.
   e2e   : the same solve with HOST buffers (pinned): H2D of b and D2H of x inside the timed region.
 N > 1 (torchrun, one process per GPU): row slabs of one larger grid, n_G = even(round(n * sqrt(G))), so the
-unknowns per GPU stay fixed (weak scaling); halo rows and scalar reductions go over NCCL inside the library.
+unknowns per GPU stay fixed (weak scaling, BASELINE.json configs[4]); halo rows and scalar reductions go over NVLink
+peer memory (NCCL as fallback) inside the library. --scaling strong shards the fixed --grid-n grid instead (configs[2]).
+Workload at N = 1: the 16384^2 grid - the configuration BASELINE.json quotes its metric and target on ("a 16384^2 fp64
+Dirichlet CG solve at >= 70 % of B200 HBM bandwidth per GPU"; configs[2] and [4] at one GPU); it fits one GPU (17 GB).
+configs[1] (4096^2) and configs[3] (CSR, 8192^2) run with --grid-n 4096 / --op csr --grid-n 8192 and are parity-test cases.
 
 --impl reference times the reference's own CPU solver (unmodified sources compiled into oracle/_ref, else the
 C port in oracle/) on a bounded sample of the same workload, on rank 0 only.
