@@ -40,6 +40,11 @@ struct FusedCfg {
   static constexpr bool EDGE = (FLAGS & F_EDGE) != 0;
   static constexpr int NS = EDGE ? 3 : 2;           // gamma', delta'  |  gamma', horizontal, vertical edge sums
   static constexpr int ROWS_BELOW = EDGE ? 1 : 2;   // rows streamed below a tile's first emit row
+  // F_SHARD (sharded plans, peer memory; B200CG_SINGLE_SWEEP_SHARDED=1, not yet run on hardware): the slab's two
+  // first / last rows of r' and p also go to the neighbours - into their halo row and into one of the two extra rows
+  // every pitched vector carries behind its stored rows (row ylo-2 at index yrows, row yhi+1 at index yrows+1) - and
+  // the iteration's two sums cross the ranks through the PeerSync slots, alternating the slot by iteration parity.
+  static constexpr bool SHARD = (FLAGS & F_SHARD) != 0;
 };
 
 template <int FLAGS, int HS, int NST>
@@ -76,7 +81,7 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
 template <int FLAGS, int HS, int NST, int CTAS>
 __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const TileArgs a) {
   using Cfg = FusedCfg<FLAGS>;
-  constexpr bool X2 = Cfg::X2, EDGE = Cfg::EDGE;
+  constexpr bool X2 = Cfg::X2, EDGE = Cfg::EDGE, SHARD = Cfg::SHARD;
   constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
   constexpr int STAGE_DOUBLES = HS * NSTREAM * STRIP_LOAD;
   constexpr int OFF_P = 0, OFF_R = HS * STRIP_LOAD, OFF_X = 2 * HS * STRIP_LOAD;
@@ -105,7 +110,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
 
   double acc_s[NS] = {0.0};  // gamma', delta'  (F_EDGE: gamma', horizontal and vertical edge sums)
   double acc_m[1] = {0.0};
+  bool sent_halo = false;  // F_SHARD: this thread stored into a neighbour rank's rows
   const int y_store_lo = g.ybase, y_store_hi = g.ybase + g.yrows;  // stored rows [lo, hi)
+  // Row index of grid row y inside a pitched vector, or -1 where the row does not exist (beyond the domain boundary).
+  auto row_index = [&](int y) -> int {
+    if (y >= y_store_lo && y < y_store_hi) return y - g.ybase;
+    if (SHARD && y == g.ylo - 2 && a.nb_r_below) return g.yrows;      // second halo row below (from the neighbour)
+    if (SHARD && y == g.yhi + 1 && a.nb_r_above) return g.yrows + 1;  // second halo row above
+    return -1;
+  };
 
   if (warp == CONS_WARPS) {
     // ================================================================ producer
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
           int stored = 0, inner = 0;
           for (int j = 0; j < nrows; ++j) {
             const int y = y0 + j;
-            stored += (y >= y_store_lo && y < y_store_hi) ? 1 : 0;
+            stored += (row_index(y) >= 0) ? 1 : 0;
             inner += (y >= ya && y < yb) ? 1 : 0;
           }
           const uint32_t bytes = row_bytes * (uint32_t)(2 * stored + (X2 ? inner : 0));
@@ -140,8 +153,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
           double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
           for (int j = 0; j < nrows; ++j) {
             const int y = y0 + j;
-            if (y < y_store_lo || y >= y_store_hi) continue;
-            const size_t off = (size_t)(y - g.ybase) * pitch + (size_t)col0;
+            const int ri = row_index(y);
+            if (ri < 0) continue;
+            const size_t off = (size_t)ri * pitch + (size_t)col0;
             bulk_g2s(sd + OFF_P + j * STRIP_LOAD, a.p_in + off, row_bytes, &full[stage]);
             bulk_g2s(sd + OFF_R + j * STRIP_LOAD, a.r_in + off, row_bytes, &full[stage]);
             if (X2 && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * STRIP_LOAD, a.x + off, row_bytes, &full[stage]);
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
           cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * STRIP_LOAD + sc);
           if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + sc);
         } else {
-          const bool row_stored = (y >= y_store_lo) && (y < y_store_hi);
+          const bool row_stored = row_index(y) >= 0;
           const bool row_ok = (y >= 1) && (y <= g.m - 1);
           const int xlo = (g.ysplit != 0 && y <= g.ysplit) ? g.xsplit + 1 : 1;
           k0a = row_ok && (x0 >= xlo) && (x0 <= g.n - 1);
@@ -261,6 +275,24 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
               xn.y = __dadd_rn(__dadd_rn(x1.y, __dmul_rn(alpha_prev, q1.y)), __dmul_rn(alpha, P1.y));
               st2_out(a.x + o, xn);
             }
+            if (SHARD && !FULL) {
+              // the slab's two first / last rows also land in the neighbours' halo rows (NVLink stores)
+              const int ye = y - 1;
+              if (a.nb_r_below && (ye == g.ylo || ye == g.ylo + 1)) {
+                double* dr = (ye == g.ylo ? a.nb_r_below : a.nb_r_below2) + col_off;
+                double* dp = (ye == g.ylo ? a.nb_p_below : a.nb_p_below2) + col_off;
+                st2(dr, R0);
+                st2(dp, P1);
+                sent_halo = true;
+              }
+              if (a.nb_r_above && (ye == g.yhi - 1 || ye == g.yhi - 2)) {
+                double* dr = (ye == g.yhi - 1 ? a.nb_r_above : a.nb_r_above2) + col_off;
+                double* dp = (ye == g.yhi - 1 ? a.nb_p_above : a.nb_p_above2) + col_off;
+                st2(dr, R0);
+                st2(dp, P1);
+                sent_halo = true;
+              }
+            }
           }
           acc_s[0] = fma(R0.x, R0.x, acc_s[0]);
           acc_s[0] = fma(R0.y, R0.y, acc_s[0]);
@@ -295,7 +327,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
         r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
         k1a = k0a;  k1b = k0b;
       };
-      if (m.nrows == HS && m.y0 >= ya + 2 && m.y0 + HS <= yb) {
+      // (sharded plans: the emit rows ya+1 and yb-2 may be rows the neighbours need, so FULL stays clear of them)
+      if (m.nrows == HS && m.y0 >= ya + (SHARD ? 3 : 2) && m.y0 + HS <= yb - (SHARD ? 1 : 0)) {
 #pragma unroll
         for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
       } else {
@@ -309,9 +342,21 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
   }
 
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
+  if (SHARD && sent_halo) __threadfence_system();  // remote halo stores before the exit ticket
   if (!grid_reduce<NS, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
-  const double delta = EDGE ? g.A * acc_s[0] + 2.0 * g.xk * acc_s[1] + 2.0 * g.yk * acc_s[NS - 1] : acc_s[1];
-  finalize_fused(st, acc_s[0], delta, FLAGS);
+  double gamma = acc_s[0];
+  double delta = EDGE ? g.A * acc_s[0] + 2.0 * g.xk * acc_s[1] + 2.0 * g.yk * acc_s[NS - 1] : acc_s[1];  // (linear in the sums)
+  if (SHARD) {
+    // this rank's two sums to every rank, everyone's back; the slot alternates with the iteration parity so that a fast
+    // rank's next publication cannot overwrite values a slow rank is still reading
+    const int phase = X2 ? 1 : 0;
+    double mine[2] = {gamma, delta}, none[1] = {0.0}, total[4];
+    peer_publish<2, 0>(a.peers, st, phase, mine, none);
+    if (!peer_collect(st, a.peers, phase, total)) return;
+    gamma = total[0];
+    delta = total[1];
+  }
+  finalize_fused(st, gamma, delta, FLAGS);
 }
 
 }  // namespace b200cg

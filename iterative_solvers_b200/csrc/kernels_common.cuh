@@ -24,7 +24,8 @@ enum {
   F_SUB_B = 4,   // APPLY: out = A v - b
   F_NOX = 8,     // UPD, x-deferral: even iteration, x is not touched (its update stays pending)
   F_X2 = 16,     // UPD, x-deferral: odd iteration, applies the pending update and this one
-  F_EDGE = 32    // single-sweep kernel: r'.A r' from edge sums instead of a second stencil (fused_kernel.cuh)
+  F_EDGE = 32,   // single-sweep kernel: r'.A r' from edge sums instead of a second stencil (fused_kernel.cuh)
+  F_SHARD = 64   // single-sweep kernel on a sharded plan: two halo rows per side over peer memory
 };
 
 struct TileArgs {
@@ -48,6 +49,11 @@ struct TileArgs {
   double* nb_p_below;
   double* nb_r_above;  // neighbour above: start of its bottom halo row
   double* nb_p_above;
+  // single-sweep kernel on sharded plans: the neighbours' second halo rows (the two extra rows behind their stored rows)
+  double* nb_r_below2;
+  double* nb_p_below2;
+  double* nb_r_above2;
+  double* nb_p_above2;
   unsigned long long* cta_clock;  // [2 * gridDim.x] globaltimer at CTA start / end of its sweep (load balancing)
   Geom g;
 };
@@ -291,6 +297,39 @@ __device__ __forceinline__ void peer_finalize(DevState* st, CbRecord* log, const
                     (report && has_u) ? s[2] : 0.0, report);
     note_x_deferral(st, flags);
   }
+}
+
+// The wait half of peer_finalize alone (single-sweep kernel): true when every rank's publication of this epoch of
+// `phase` has landed; the summed slots come back in s[0..3]. On a timeout the solve is ended with comm_error.
+__device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, int phase, double (&s)[4]) {
+  const unsigned long long epoch = st->epoch[phase] + 1ull;
+  const PeerSync* mine = pl->sync[pl->rank];
+  bool ok = true;
+  const unsigned long long t0 = global_ns();
+  for (int r = 0; r < pl->world && ok; ++r) {
+    const volatile unsigned long long* f = &mine->flag[phase][r];
+    while (*f < epoch) {
+      if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+        ok = false;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  st->epoch[phase] = epoch;
+  if (!ok) {
+    st->comm_error = 1;
+    st->done = 1;
+    st->converged = 0;
+    return false;
+  }
+  s[0] = s[1] = s[2] = s[3] = 0.0;
+  for (int r = 0; r < pl->world; ++r) {
+    const volatile double* v = mine->vals[phase][r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] += v[k];
+  }
+  return true;
 }
 
 }  // namespace b200cg

@@ -402,7 +402,8 @@ static int plan_create_impl(b200cg_plan_s* P) {
   const Geom& g = P->g;
   P->generic = P->desc.domain == B200CG_DOMAIN_GENERIC;
   if (!P->generic) {
-    P->vec_elems = (size_t)g.yrows * (size_t)g.pitch;
+    // + two rows behind the stored ones: the second halo rows (ylo-2, yhi+1) of the sharded single-sweep iteration
+    P->vec_elems = (size_t)(g.yrows + 2) * (size_t)g.pitch;
     for (int i = 0; i < 2; ++i) {
       RET(alloc_vec(P, &P->r[i]));
       RET(alloc_vec(P, &P->p[i]));
@@ -434,6 +435,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
     P->shape_fused = env_int("B200CG_SHAPE_FUSED", P->shape_fused);
     P->fused_edge_sums = env_int("B200CG_FUSED_DELTA", 0) != 0;
+    P->fused_sharded = env_int("B200CG_SINGLE_SWEEP_SHARDED", 0) != 0;
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->balance_rounds_fused = P->balance_rounds;

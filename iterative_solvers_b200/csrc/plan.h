@@ -81,6 +81,8 @@ struct b200cg_plan_s {
   int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int balance_rounds_fused = 0;  // the same for the single-sweep flavour, counted from its own first launches
   int shape_fused = 0;                              // single-sweep kernel: 0 = 4-row stages, 1 = 3-row stages
+  bool fused_sharded = false;                       // single-sweep iteration on sharded plans (B200CG_SINGLE_SWEEP_SHARDED=1;
+                                                    // written against the CPU model only, not yet run on hardware)
   bool fused_edge_sums = false;                     // single-sweep kernel: r'.A r' from edge sums (B200CG_FUSED_DELTA=1)
   int shape_dot = 3, shape_upd = 2, shape_nox = 2;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration

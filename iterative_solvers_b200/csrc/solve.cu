@@ -58,17 +58,6 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     a.r_out = P->r[par ^ 1];
     a.p_out = P->p[par ^ 1];
     a.u = P->u;
-    if (fused) {
-      // single-sweep iteration: one kernel; x touched on odd iterations only (the event slots of the absent dot
-      // phase collapse to zero length)
-      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
-      if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
-      rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
-      ++kernels;
-      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
-      if (k == 1) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
-      continue;
-    }
     const int fl = xdefer ? ((k & 1) ? F_X2 : F_NOX) : ((with_u ? F_U : 0) | (report ? F_REPORT : 0));
     // sharded plans: reductions and halo rows over NVLink peer memory (no NCCL call in the loop); the per-iteration
     // report variant keeps the NCCL exchange
@@ -82,11 +71,27 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
         const size_t rows_below = (size_t)(P->ycuts[rank] - P->ycuts[rank - 1]) + 2;
         a.nb_r_below = P->nb_below_r[par ^ 1] + (rows_below - 1) * g.pitch;
         a.nb_p_below = P->nb_below_p[par ^ 1] + (rows_below - 1) * g.pitch;
+        a.nb_r_below2 = P->nb_below_r[par ^ 1] + (rows_below + 1) * g.pitch;  // its second extra row (its yhi+1)
+        a.nb_p_below2 = P->nb_below_p[par ^ 1] + (rows_below + 1) * g.pitch;
       }
       if (rank + 1 < P->desc.world) {  // neighbour above: its bottom halo row is its stored row 0
+        const size_t rows_above = (size_t)(P->ycuts[rank + 2] - P->ycuts[rank + 1]) + 2;
         a.nb_r_above = P->nb_above_r[par ^ 1];
         a.nb_p_above = P->nb_above_p[par ^ 1];
+        a.nb_r_above2 = P->nb_above_r[par ^ 1] + rows_above * g.pitch;  // its first extra row (its ylo-2)
+        a.nb_p_above2 = P->nb_above_p[par ^ 1] + rows_above * g.pitch;
       }
+    }
+    if (fused) {
+      // single-sweep iteration: one kernel; x touched on odd iterations only (the event slots of the absent dot
+      // phase collapse to zero length)
+      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+      if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
+      rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
+      ++kernels;
+      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+      if (k == 1) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
+      continue;
     }
     rc = launch_tile<MODE_DOT, 0>(P, a, s);
     ++kernels;
@@ -365,6 +370,20 @@ static int launch_init(SolveCall& c) {
     a.p_in = P->p[0];
     RET((launch_tile<MODE_DOT, 0>(P, a, s)));
     c.info->kernel_launches += 1;
+    if (P->desc.world > 1) {
+      // sharded plan: the dot sweep left this rank's sums in loc_s (defer = 1); then the second halo rows of the first
+      // sweep's inputs: r0 from the neighbours (their second first / last rows), p = 0
+      RET(reduce_and_finalize(P, 1, 0, false, s));
+      c.info->kernel_launches += 1;
+      const Geom& g = P->g;
+      double* r0 = P->r[0];
+      double* extra_r = r0 + (size_t)g.yrows * g.pitch;
+      std::string err;
+      if (!comm_halo(&P->comm, r0 + (size_t)2 * g.pitch, r0 + (size_t)(g.yrows - 3) * g.pitch, extra_r, extra_r + g.pitch,
+                     g.pitch, s, &err))
+        return fail(B200CG_ERR_COMM, "%s", err.c_str());
+      CU(cudaMemsetAsync(P->p[0] + (size_t)g.yrows * g.pitch, 0, (size_t)2 * g.pitch * sizeof(double), s));
+    }
   }
   return B200CG_OK;
 }
@@ -399,7 +418,12 @@ static int run_graph_solve(SolveCall& c) {
   cudaStream_t s = P->stream;
   // single-sweep iteration (opt-in): relative-residual rule without report on an unsharded plan
   const bool want_fused = prm->single_sweep == 1 || (prm->single_sweep == 0 && P->single_sweep_default);
-  c.fused = want_fused && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2 && P->desc.world <= 1;
+  bool fused_ok = P->desc.world <= 1;
+  if (!fused_ok && P->fused_sharded && P->peer_mode) {  // sharded: every rank must own >= 4 rows (all ranks see all cuts)
+    fused_ok = true;
+    for (int r = 0; r < P->desc.world; ++r) fused_ok = fused_ok && (P->ycuts[r + 1] - P->ycuts[r] >= 4);
+  }
+  c.fused = want_fused && fused_ok && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2;
   RET(launch_init(c));
   int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
   if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);

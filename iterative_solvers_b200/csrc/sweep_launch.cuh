@@ -102,6 +102,8 @@ static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  if (a.defer == 2)  // sharded plan, peer memory (default shape, stencil form only)
+    return launch_fused_shape<FLAGS | F_SHARD, 0>(P, a, s);
   if (P->fused_edge_sums)  // B200CG_FUSED_DELTA=1 (tuning variant): r'.A r' from edge sums
     return P->shape_fused == 1 ? launch_fused_shape<FLAGS | F_EDGE, 1>(P, a, s) : launch_fused_shape<FLAGS | F_EDGE, 0>(P, a, s);
   return P->shape_fused == 1 ? launch_fused_shape<FLAGS, 1>(P, a, s) : launch_fused_shape<FLAGS, 0>(P, a, s);

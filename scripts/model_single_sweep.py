@@ -63,9 +63,35 @@ class Grid:
         return out
 
 
-def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, edge=False):
+class Slab:
+    """One rank of a sharded plan: rows ylo-1 .. yhi stored at row index y - ybase, plus the two extra rows behind them
+    (index yrows: row ylo-2, index yrows+1: row yhi+1) that the single-sweep kernel uses as second halo rows."""
+
+    def __init__(self, G, ylo, yhi, below, above):
+        self.ylo, self.yhi, self.ybase, self.yrows = ylo, yhi, ylo - 1, yhi - ylo + 2
+        self.has_below, self.has_above = below, above
+        shape = (self.yrows + 2, G.pitch)
+        self.r = [np.zeros(shape), np.zeros(shape)]
+        self.p = [np.zeros(shape), np.zeros(shape)]
+        self.x = np.zeros(shape)
+
+    def row_index(self, y):
+        if self.ybase <= y < self.ybase + self.yrows:
+            return y - self.ybase
+        if y == self.ylo - 2 and self.has_below:
+            return self.yrows
+        if y == self.yhi + 1 and self.has_above:
+            return self.yrows + 1
+        return -1
+
+
+def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, edge=False, slab=None, nb_below=None,
+          nb_above=None):
     """One launch of the kernel over all tiles; returns (gamma', delta'). edge: the F_EDGE variant (r'.A r' from
-    edge sums, rows streamed from ya-1)."""
+    edge sums, rows streamed from ya-1). slab / nb_*: the F_SHARD variant - this rank's Slab and the (r_out, p_out)
+    arrays of the neighbour ranks, whose halo rows receive this slab's two first / last rows."""
+    if slab is None:
+        slab = Slab(G, 1, G.m, False, False)  # one rank owning every row: rows 0 .. m stored, no extra rows in use
     warp = np.arange(8)[:, None]
     lane = np.arange(32)[None, :]
     sc = WARP_STEP * warp + 2 * lane
@@ -89,7 +115,8 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
         r1x, r1y, x1x, x1y, q1x, q1y = z, z, z, z, z, z
         k1a = k1b = np.zeros((8, 32), dtype=bool)
         for y in range(ya - (1 if edge else 2), yb + 2):
-            stored = G.ybase <= y < G.ybase + G.yrows
+            ri = slab.row_index(y)
+            stored = ri >= 0
             row_ok = 1 <= y <= G.m - 1
             xlo = G.xsplit + 1 if (G.ysplit != 0 and y <= G.ysplit) else 1
             k0a = row_ok & (x0 >= xlo) & (x0 <= G.n - 1)
@@ -97,7 +124,7 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
             if stored:
                 def stage(src):
                     buf = np.full(STRIP_LOAD, np.nan)  # what the bulk copy does not write stays stale
-                    buf[:row_doubles] = src[y - G.ybase, col0:col0 + row_doubles]
+                    buf[:row_doubles] = src[ri, col0:col0 + row_doubles]
                     return buf
                 sp, sr = stage(p_in), stage(r_in)
                 cpx, cpy, crx, cry = sp[sc], sp[sc + 1], sr[sc], sr[sc + 1]
@@ -120,9 +147,20 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
             if ya <= y - 1 < yb:
                 st = writer & (k1a | k1b)
                 cols = (col0 + sc)[st]
-                yy = y - 1 - G.ybase
+                yy = y - 1 - slab.ybase
                 r_out[yy, cols], r_out[yy, cols + 1] = R0x[st], R0y[st]
                 p_out[yy, cols], p_out[yy, cols + 1] = P1x[st], P1y[st]
+                ye = y - 1
+                if nb_below is not None and ye in (slab.ylo, slab.ylo + 1):  # its top halo row / its second extra row
+                    nb, rows = nb_below
+                    row = rows - 1 if ye == slab.ylo else rows + 1
+                    for arr, vx, vy in ((nb[0], R0x, R0y), (nb[1], P1x, P1y)):
+                        arr[row, cols], arr[row, cols + 1] = vx[st], vy[st]
+                if nb_above is not None and ye in (slab.yhi - 1, slab.yhi - 2):  # its bottom halo row / first extra row
+                    nb, rows = nb_above
+                    row = 0 if ye == slab.yhi - 1 else rows
+                    for arr, vx, vy in ((nb[0], R0x, R0y), (nb[1], P1x, P1y)):
+                        arr[row, cols], arr[row, cols + 1] = vx[st], vy[st]
                 if x2:
                     x[yy, cols] = ((x1x + alpha_prev * q1x) + alpha * P1x)[st]
                     x[yy, cols + 1] = ((x1y + alpha_prev * q1y) + alpha * P1y)[st]
@@ -194,6 +232,68 @@ def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False):
     return worst, dx, dr, len(tiles)
 
 
+def run_sharded(n, m, lshape, iters, world, sms=4, tile_rows=0):
+    """The F_SHARD data flow: `world` row slabs, each sweeping its own tiles, the two first / last rows of r' and p stored
+    into the neighbours' halo row and extra row, the sums added over the ranks. Compared with one global CG."""
+    G = Grid(n, m, lshape)
+    domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
+    rng = np.random.default_rng(n * 1000 + m)
+    b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+    bp = G.to_pitched(b)
+    slabs, tiles = [], []
+    for rank in range(world):
+        ylo, yhi, _lo, _hi, _n = capi.partition(m, n, domain=domain, rank=rank, world=world)
+        assert yhi - ylo >= 4
+        sl = Slab(G, ylo, yhi, rank > 0, rank + 1 < world)
+        for y in range(ylo - 2, yhi + 2):  # r0 = b incl. both halo rows (what the initial exchanges deliver)
+            ri = sl.row_index(y)
+            if ri >= 0:
+                sl.r[0][ri] = bp[y]
+        slabs.append(sl)
+        tiles.append(capi.work_split(m, n, domain=domain, rank=rank, world=world, sms=sms, ctas_per_sm=2,
+                                     tile_rows=tile_rows, fused=True)[0])
+
+    r = b.copy(); p = np.zeros_like(b); xs = np.zeros_like(b)
+    gamma = float(np.sum(r * r)); alpha = gamma / float(np.sum(r * G.apply(r))); beta = 0.0
+    hist = []
+    for _ in range(iters):
+        p = r + beta * p
+        xs = xs + alpha * p
+        r = r - alpha * G.apply(p)
+        g2 = float(np.sum(r * r)); d2 = float(np.sum(r * G.apply(r)))
+        hist.append((g2, d2))
+        beta = g2 / gamma
+        alpha = g2 / (d2 - beta * g2 / alpha)
+        gamma = g2
+
+    gamma = float(np.sum(b * b)); alpha = gamma / float(np.sum(b * G.apply(b))); beta = 0.0; alpha_prev = 0.0
+    worst = 0.0
+    for k in range(iters):
+        par = k & 1
+        g2 = d2 = 0.0
+        for rank, sl in enumerate(slabs):
+            below = slabs[rank - 1] if rank > 0 else None
+            above = slabs[rank + 1] if rank + 1 < world else None
+            gg, dd = sweep(G, tiles[rank], sl.r[par], sl.p[par], sl.x, sl.r[par ^ 1], sl.p[par ^ 1], alpha, beta, alpha_prev,
+                           x2=bool(k & 1), slab=sl,
+                           nb_below=((below.r[par ^ 1], below.p[par ^ 1]), below.yrows) if below else None,
+                           nb_above=((above.r[par ^ 1], above.p[par ^ 1]), above.yrows) if above else None)
+            g2 += gg
+            d2 += dd
+        worst = max(worst, abs(g2 - hist[k][0]) / hist[k][0], abs(d2 - hist[k][1]) / abs(hist[k][1]))
+        alpha_prev = alpha if not (k & 1) else 0.0
+        beta = g2 / gamma
+        alpha, gamma = g2 / (d2 - beta * g2 / alpha), g2
+    xg = np.zeros((m + 1, G.pitch)); rg = np.zeros((m + 1, G.pitch))
+    for sl in slabs:
+        xo = sl.x + (alpha_prev * sl.p[iters & 1] if iters & 1 else 0.0)  # x_flush_kernel
+        xg[sl.ylo:sl.yhi] = xo[1:1 + sl.yhi - sl.ylo]
+        rg[sl.ylo:sl.yhi] = sl.r[iters & 1][1:1 + sl.yhi - sl.ylo]
+    xr, rr = G.from_pitched(xg), G.from_pitched(rg)
+    assert np.all(np.isfinite(xr)) and not np.any(xr[~G.mask]) and not np.any(rr[~G.mask])
+    return worst, np.max(np.abs(xr - xs)) / np.max(np.abs(xs)), np.max(np.abs(rr - r)) / np.max(np.abs(r))
+
+
 if __name__ == "__main__":
     for n, m, lshape, iters, tr in [(30, 30, True, 7, 0), (64, 64, True, 6, 0), (64, 64, True, 5, 5), (130, 90, True, 6, 0),
                                     (77, 33, False, 6, 3), (1000, 40, True, 4, 0), (970, 24, False, 3, 7)]:
@@ -203,4 +303,9 @@ if __name__ == "__main__":
                   f"dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
             # the edge-sum form of r'.A r' cancels A_diag * gamma' against the edge terms: its dots carry ~1e-11
             assert worst < (1e-9 if edge else 1e-12) and dx < 1e-10 and dr < 1e-10
+    for n, m, lshape, iters, world, tr in [(64, 64, True, 6, 2, 0), (64, 64, True, 5, 3, 0), (130, 90, True, 5, 4, 0),
+                                           (77, 60, False, 5, 3, 5), (1000, 40, True, 4, 2, 0), (96, 96, True, 7, 8, 0)]:
+        worst, dx, dr = run_sharded(n, m, lshape, iters, world, tile_rows=tr)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} {world} slabs tile_rows={tr}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
+        assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
     print("MODEL_OK")

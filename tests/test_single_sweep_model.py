@@ -25,3 +25,12 @@ def test_model_matches_plain_single_reduction_cg(model, n, m, lshape, iters, til
     worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows, edge=edge)
     assert ntiles >= 1
     assert worst < 1e-9 and dx < 1e-10 and dr < 1e-10
+
+
+@pytest.mark.parametrize("n,m,lshape,iters,world,tile_rows", [(64, 64, True, 5, 2, 0), (70, 60, True, 4, 3, 0),
+                                                              (77, 60, False, 4, 3, 5), (96, 96, True, 4, 8, 0)])
+def test_sharded_model(model, n, m, lshape, iters, world, tile_rows):
+    """F_SHARD: row slabs with two halo rows per side (the neighbours' halo row + one of the two extra rows behind the
+    stored rows), filled by the neighbours' sweeps; sums added over the ranks."""
+    worst, dx, dr = model.run_sharded(n, m, lshape, iters, world, tile_rows=tile_rows)
+    assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
