@@ -136,7 +136,7 @@ def work_split(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1, sms=148, ctas_per_sm
     fused: the single-sweep kernel's strip geometry (480 written columns from storage column strip * 480 + 2).
     Pure host logic (b200cg_work_split) - works without a GPU."""
     desc = PlanDesc(n=int(n), m=int(m), a=0.0, b=1.0, c=0.0, d=1.0, domain=int(domain), device=0, rank=int(rank),
-                    world=int(world), tile_rows=int(tile_rows), reserved0=1 if fused else 0)
+                    world=int(world), tile_rows=int(tile_rows), reserved0=int(fused))  # 2: the 7-warp variant (420 columns)
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     nw = 0 if w is None else int(w.size)
     count, grid = C.c_int64(), C.c_int()

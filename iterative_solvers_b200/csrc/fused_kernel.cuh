@@ -24,10 +24,11 @@
 
 namespace b200cg {
 
-constexpr int FUSED_STRIP_OUT = 480;    // columns written per strip
-constexpr int FUSED_STRIP_COLS = 484;   // columns staged: two halo columns per side
-constexpr int FUSED_COL_SHIFT = 2;      // a strip's first staged storage column is strip * FUSED_STRIP_OUT + this
 constexpr int FUSED_WARP_STEP = 60;     // columns written per consumer warp (64 processed)
+constexpr int FUSED_COL_SHIFT = 2;      // a strip's first staged storage column is strip * (columns written) + this
+constexpr int FUSED_STRIP_OUT = FUSED_WARP_STEP * CONS_WARPS;  // 480 columns written per strip (8 consumer warps)
+// CW consumer warps (template parameter, default 8; 7 is a tuning variant: an 8-warp CTA may use 128 registers)
+constexpr int fused_strip_out(int cw) { return FUSED_WARP_STEP * cw; }  // (host side: plan.cu)
 
 template <int FLAGS>
 struct FusedCfg {
@@ -78,8 +79,8 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
   st->pAp = gamma_new / alpha;
 }
 
-template <int FLAGS, int HS, int NST, int CTAS>
-__global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const TileArgs a) {
+template <int FLAGS, int HS, int NST, int CTAS, int CW = CONS_WARPS>
+__global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const TileArgs a) {
   using Cfg = FusedCfg<FLAGS>;
   constexpr bool X2 = Cfg::X2, EDGE = Cfg::EDGE, SHARD = Cfg::SHARD;
   constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CONS_WARPS);
+      mbar_init(&empty[i], CW);
     }
     mbar_fence_init();
     if (a.cta_clock) a.cta_clock[2 * blockIdx.x] = global_ns();
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
     return -1;
   };
 
-  if (warp == CONS_WARPS) {
+  if (warp == CW) {
     // ================================================================ producer
     if (lane == 0) {
       int stage = 0;
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_fused_kernel(const Ti
       for (int t = a.cta_begin[blockIdx.x]; t < t_end; ++t) {
         const Tile tl = a.tiles[t];
         const int col0 = tl.col0, ya = tl.ya, yb = tl.yb;
-        const uint32_t row_bytes = (uint32_t)min(FUSED_STRIP_COLS, g.pitch - col0) * 8u;
+        constexpr int STRIP_COLS = FUSED_WARP_STEP * CW + 4;  // staged columns: two halo columns per side
+        const uint32_t row_bytes = (uint32_t)min(STRIP_COLS, g.pitch - col0) * 8u;
         const int S = yb - ya + 2 + LO;  // rows ya-2 .. yb+1 (F_EDGE: ya-1 .. yb+1)
         for (int s0 = 0; s0 < S; s0 += HS) {
           mbar_wait(&empty[stage], phase ^ 1u);

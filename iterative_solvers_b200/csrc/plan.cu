@@ -469,7 +469,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->tile_tab[1].ctas_per_sm = ctas_of(P->shape_nox);
     P->tile_tab[2].ctas_per_sm = 2;  // every other flavour runs a 2-CTAs/SM shape
     P->tile_tab[3].ctas_per_sm = 2;  // single-sweep iteration: its own strip geometry (fused_kernel.cuh)
-    P->tile_tab[3].strip_out = FUSED_STRIP_OUT;
+    P->tile_tab[3].strip_out = P->shape_fused == 2 ? fused_strip_out(7) : FUSED_STRIP_OUT;
     P->tile_tab[3].col_shift = FUSED_COL_SHIFT;
     if (P->shape_upd == 1) P->shape_upd = 0;
     for (auto& tt : P->tile_tab) RET(upload_tiles(P, &tt));
@@ -547,8 +547,8 @@ extern "C" int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas
   tmp.sms = sms;
   TileTable tt;
   tt.ctas_per_sm = ctas_per_sm;
-  if (desc->reserved0 == 1) {  // the single-sweep kernel's strip geometry
-    tt.strip_out = FUSED_STRIP_OUT;
+  if (desc->reserved0 == 1 || desc->reserved0 == 2) {  // the single-sweep kernel's strip geometry (2: 7 consumer warps)
+    tt.strip_out = desc->reserved0 == 2 ? fused_strip_out(7) : FUSED_STRIP_OUT;
     tt.col_shift = FUSED_COL_SHIFT;
   }
   if (weights && n_weights > 0) tt.weight.assign(weights, weights + n_weights);

@@ -80,7 +80,7 @@ struct b200cg_plan_s {
   TileTable tile_tab[4];  // sweep work lists per flavour
   int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int balance_rounds_fused = 0;  // the same for the single-sweep flavour, counted from its own first launches
-  int shape_fused = 0;                              // single-sweep kernel: 0 = 4-row stages, 1 = 3-row stages
+  int shape_fused = 0;                              // single-sweep kernel: 0 = 4-row stages, 1 = 3-row stages, 2 = 7 consumer warps
   bool fused_sharded = false;                       // single-sweep iteration on sharded plans (B200CG_SINGLE_SWEEP_SHARDED=1;
                                                     // written against the CPU model only, not yet run on hardware)
   bool fused_edge_sums = false;                     // single-sweep kernel: r'.A r' from edge sums (B200CG_FUSED_DELTA=1)

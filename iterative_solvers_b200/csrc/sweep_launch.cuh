@@ -82,7 +82,8 @@ template <int FLAGS, int SHAPE>
 static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   constexpr bool X2 = FusedCfg<FLAGS>::X2;
   constexpr int HS = SHAPE == 1 ? 3 : 4, NST = SHAPE == 1 ? (X2 ? 3 : 4) : (X2 ? 2 : 3), CTAS = 2;
-  auto kernel = cg_fused_kernel<FLAGS, HS, NST, CTAS>;
+  constexpr int CW = SHAPE == 2 ? 7 : CONS_WARPS;  // shape 2: 7 consumer warps = 8-warp CTAs (128-register budget)
+  auto kernel = cg_fused_kernel<FLAGS, HS, NST, CTAS, CW>;
   constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST>();
   static thread_local bool configured[64] = {};
   const int dev = P->desc.device & 63;
@@ -96,16 +97,22 @@ static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   a.cta_begin = tt.d_cta_begin;
   a.cta_clock = P->d_clock[3];
   P->clock_ctas[3] = tt.grid;
-  kernel<<<tt.grid, STREAM_THREADS, smem, s>>>(a);
+  kernel<<<tt.grid, (CW + 1) * 32, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (a.defer == 2)  // sharded plan, peer memory (default shape, stencil form only)
+  if (a.defer == 2) {  // sharded plan, peer memory (default shape, stencil form only)
+    if (P->shape_fused == 2) return fail(B200CG_ERR_UNSUPPORTED, "B200CG_SHAPE_FUSED=2 has no sharded variant");
     return launch_fused_shape<FLAGS | F_SHARD, 0>(P, a, s);
-  if (P->fused_edge_sums)  // B200CG_FUSED_DELTA=1 (tuning variant): r'.A r' from edge sums
+  }
+  // the tile table of flavour 3 was cut for the shape's strip width when the plan was created (plan.cu)
+  if (P->fused_edge_sums) {  // B200CG_FUSED_DELTA=1 (tuning variant): r'.A r' from edge sums
+    if (P->shape_fused == 2) return launch_fused_shape<FLAGS | F_EDGE, 2>(P, a, s);
     return P->shape_fused == 1 ? launch_fused_shape<FLAGS | F_EDGE, 1>(P, a, s) : launch_fused_shape<FLAGS | F_EDGE, 0>(P, a, s);
+  }
+  if (P->shape_fused == 2) return launch_fused_shape<FLAGS, 2>(P, a, s);
   return P->shape_fused == 1 ? launch_fused_shape<FLAGS, 1>(P, a, s) : launch_fused_shape<FLAGS, 0>(P, a, s);
 }
 

@@ -86,16 +86,17 @@ class Slab:
 
 
 def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, edge=False, slab=None, nb_below=None,
-          nb_above=None):
+          nb_above=None, warps=8):
     """One launch of the kernel over all tiles; returns (gamma', delta'). edge: the F_EDGE variant (r'.A r' from
     edge sums, rows streamed from ya-1). slab / nb_*: the F_SHARD variant - this rank's Slab and the (r_out, p_out)
     arrays of the neighbour ranks, whose halo rows receive this slab's two first / last rows."""
     if slab is None:
         slab = Slab(G, 1, G.m, False, False)  # one rank owning every row: rows 0 .. m stored, no extra rows in use
-    warp = np.arange(8)[:, None]
+    warp = np.arange(warps)[:, None]  # consumer warps (8, or 7 in the B200CG_SHAPE_FUSED=2 variant)
     lane = np.arange(32)[None, :]
     sc = WARP_STEP * warp + 2 * lane
     writer = (lane >= 1) & (lane <= 30) & (warp >= 0)
+    strip_cols = WARP_STEP * warps + 4
     gam = dlt = dh = dv = 0.0
 
     def stencil(c, l, r, t, b):
@@ -107,13 +108,13 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
         return v
 
     for col0, ya, yb, _xlo in tiles:
-        row_doubles = min(STRIP_COLS, G.pitch - col0)
+        row_doubles = min(strip_cols, G.pitch - col0)
         x0 = col0 + sc - XOFF
-        z = np.zeros((8, 32))
+        z = np.zeros((warps, 32))
         P1x, P1y, P2x, P2y, LP1, RP1 = z, z, z, z, z, z
         R1x, R1y, R2x, R2y, LR1, RR1 = z, z, z, z, z, z
         r1x, r1y, x1x, x1y, q1x, q1y = z, z, z, z, z, z
-        k1a = k1b = np.zeros((8, 32), dtype=bool)
+        k1a = k1b = np.zeros((warps, 32), dtype=bool)
         for y in range(ya - (1 if edge else 2), yb + 2):
             ri = slab.row_index(y)
             stored = ri >= 0
@@ -164,10 +165,10 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
                 if x2:
                     x[yy, cols] = ((x1x + alpha_prev * q1x) + alpha * P1x)[st]
                     x[yy, cols + 1] = ((x1y + alpha_prev * q1y) + alpha * P1y)[st]
-                w = writer & np.ones((8, 32), dtype=bool)
+                w = writer & np.ones((warps, 32), dtype=bool)
                 gam += float(np.sum(R0x[w] * R0x[w]) + np.sum(R0y[w] * R0y[w]))
             LR0, RR0 = shfl_up(R0y), shfl_down(R0x)
-            w = writer & np.ones((8, 32), dtype=bool)
+            w = writer & np.ones((warps, 32), dtype=bool)
             if edge:
                 if ya <= y - 1 < yb:
                     dh += float(np.sum(R0x[w] * R0y[w]) + np.sum(R0y[w] * RR0[w]))
@@ -186,10 +187,10 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
     return gam, dlt
 
 
-def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False):
+def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False, warps=8):
     G = Grid(n, m, lshape)
     domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
-    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2, tile_rows=tile_rows, fused=True)
+    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2, tile_rows=tile_rows, fused=2 if warps == 7 else 1)
     rng = np.random.default_rng(n * 1000 + m)
     b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
 
@@ -217,7 +218,7 @@ def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False):
     for k in range(iters):
         par = k & 1
         g2, d2 = sweep(G, tiles, rb[par], pb[par], x, rb[par ^ 1], pb[par ^ 1], alpha, beta, alpha_prev, x2=bool(k & 1),
-                       edge=edge)
+                       edge=edge, warps=warps)
         worst = max(worst, abs(g2 - hist[k][0]) / hist[k][0], abs(d2 - hist[k][1]) / abs(hist[k][1]))
         alpha_prev = alpha if not (k & 1) else 0.0
         beta = g2 / gamma
@@ -307,5 +308,9 @@ if __name__ == "__main__":
                                            (77, 60, False, 5, 3, 5), (1000, 40, True, 4, 2, 0), (96, 96, True, 7, 8, 0)]:
         worst, dx, dr = run_sharded(n, m, lshape, iters, world, tile_rows=tr)
         print(f"n={n} m={m} {'L' if lshape else 'rect'} {world} slabs tile_rows={tr}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
+        assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
+    for n, m, lshape, iters, tr in [(64, 64, True, 5, 0), (900, 30, True, 3, 0), (430, 26, False, 3, 4)]:
+        worst, dx, dr, nt = run(n, m, lshape, iters, tr, warps=7)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} 7 consumer warps: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
         assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
     print("MODEL_OK")

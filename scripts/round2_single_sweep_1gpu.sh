@@ -6,7 +6,7 @@ mkdir -p $out
 B200CG_TEST_EXPERIMENTAL=1 timeout -k 5 400 python -m pytest tests/test_single_sweep_gpu.py -m gpu -q 2>&1 | tail -15 | tee $out/tests.log
 : > $out/ab.txt
 for rep in 1 2; do
-  for v in "-" "B200CG_FUSED_DELTA=1" "B200CG_SHAPE_FUSED=1" "B200CG_FUSED_DELTA=1 B200CG_SHAPE_FUSED=1"; do
+  for v in "-" "B200CG_FUSED_DELTA=1" "B200CG_SHAPE_FUSED=1" "B200CG_SHAPE_FUSED=2" "B200CG_FUSED_DELTA=1 B200CG_SHAPE_FUSED=2"; do
     envs=""; [ "$v" != "-" ] && envs="$v"
     line=$(env $envs timeout -k 5 120 python bench.py --single-sweep 1 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1)
     python - "$v" "$line" >> $out/ab.txt <<'PY'

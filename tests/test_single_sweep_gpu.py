@@ -124,10 +124,12 @@ def test_large_grid_property(capi):
 @pytest.mark.skipif(__import__("os").environ.get("B200CG_TEST_EXPERIMENTAL") != "1",
                     reason="tuning variants of the single-sweep kernel that have only been checked by the CPU model "
                            "(scripts/model_single_sweep.py); set B200CG_TEST_EXPERIMENTAL=1 to run them")
-@pytest.mark.parametrize("env", [{"B200CG_FUSED_DELTA": "1"}, {"B200CG_SHAPE_FUSED": "1"},
-                                 {"B200CG_FUSED_DELTA": "1", "B200CG_SHAPE_FUSED": "1"}])
+@pytest.mark.parametrize("env", [{"B200CG_FUSED_DELTA": "1"}, {"B200CG_SHAPE_FUSED": "1"}, {"B200CG_SHAPE_FUSED": "2"},
+                                 {"B200CG_FUSED_DELTA": "1", "B200CG_SHAPE_FUSED": "1"},
+                                 {"B200CG_FUSED_DELTA": "1", "B200CG_SHAPE_FUSED": "2"}])
 def test_experimental_variants(capi, oracle_mod, env):
-    """r'.A r' from edge sums (no second stencil) and 3-row stages: same bar as the default single-sweep kernel."""
+    """r'.A r' from edge sums (no second stencil), 3-row stages, 7 consumer warps per CTA (420-column strips, 128
+    registers): same bar as the default single-sweep kernel."""
     import os
 
     saved = {k: os.environ.get(k) for k in env}

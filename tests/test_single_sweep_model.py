@@ -34,3 +34,10 @@ def test_sharded_model(model, n, m, lshape, iters, world, tile_rows):
     stored rows), filled by the neighbours' sweeps; sums added over the ranks."""
     worst, dx, dr = model.run_sharded(n, m, lshape, iters, world, tile_rows=tile_rows)
     assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
+
+
+@pytest.mark.parametrize("n,m,lshape,iters,tile_rows", [(64, 64, True, 4, 0), (900, 30, True, 3, 0), (430, 26, False, 3, 4)])
+def test_seven_warp_variant_model(model, n, m, lshape, iters, tile_rows):
+    """B200CG_SHAPE_FUSED=2: 7 consumer warps, strips of 420 written columns."""
+    worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows, warps=7)
+    assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
