@@ -98,3 +98,103 @@ def test_two_rank_slab_protocol(tmp_path, n, domain):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, n, domain, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+# ---------------------------------------------------------------- the sharded single-sweep iteration (F_SHARD), 2 processes
+def _single_sweep_worker(rank, world, port, n, iters, out_dir):
+    """Each process owns one slab of the lane-level kernel model (scripts/model_single_sweep.py) and runs the single-sweep
+    iteration on it; what the CUDA kernel stores into its neighbours over NVLink travels here as gloo messages, the
+    PeerSync sums as an all-reduce. The assembled iterate must equal a global single-reduction CG."""
+    sys.path.insert(0, ROOT)
+    import importlib.util
+
+    import torch
+    import torch.distributed as dist
+
+    from iterative_solvers_b200 import capi
+
+    spec = importlib.util.spec_from_file_location("model_single_sweep", os.path.join(ROOT, "scripts", "model_single_sweep.py"))
+    model = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(model)
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        G = model.Grid(n, n, True)
+        rng = np.random.default_rng(n)
+        b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+        bp = G.to_pitched(b)
+        ylo, yhi, _lo, _hi, _N = capi.partition(n, n, capi.DOMAIN_LSHAPE, rank, world)
+        sl = model.Slab(G, ylo, yhi, rank > 0, rank + 1 < world)
+        for y in range(ylo - 2, yhi + 2):  # r0 = b with both halo rows: what the init exchanges deliver
+            ri = sl.row_index(y)
+            if ri >= 0:
+                sl.r[0][ri] = bp[y]
+        tiles = capi.work_split(n, n, domain=capi.DOMAIN_LSHAPE, rank=rank, world=world, sms=4, ctas_per_sm=2, fused=True)[0]
+
+        def exchange(buf):
+            """rows ylo, ylo+1 -> the rank below (its halo row yhi, its extra row yhi+1); rows yhi-1, yhi-2 -> the rank
+            above (its halo row ylo-1, its extra row ylo-2): fused_kernel.cuh, F_SHARD stores."""
+            reqs, inbox = [], []
+            for arr in (sl.r[buf], sl.p[buf]):
+                if rank > 0:
+                    reqs.append(dist.isend(torch.from_numpy(arr[[1, 2]].copy()), rank - 1))
+                    t = torch.zeros(2, G.pitch, dtype=torch.float64)
+                    reqs.append(dist.irecv(t, rank - 1))
+                    inbox.append((arr, [0, sl.yrows], t))          # their yhi-1 -> our row ylo-1; their yhi-2 -> extra row 0
+                if rank + 1 < world:
+                    reqs.append(dist.isend(torch.from_numpy(arr[[sl.yrows - 2, sl.yrows - 3]].copy()), rank + 1))
+                    t = torch.zeros(2, G.pitch, dtype=torch.float64)
+                    reqs.append(dist.irecv(t, rank + 1))
+                    inbox.append((arr, [sl.yrows - 1, sl.yrows + 1], t))  # their ylo -> our row yhi; their ylo+1 -> extra row 1
+            for q in reqs:
+                q.wait()
+            for arr, rows, t in inbox:
+                arr[rows] = t.numpy()
+
+        gamma = float(np.sum(b * b))
+        alpha = gamma / float(np.sum(b * G.apply(b)))
+        beta = alpha_prev = 0.0
+        for k in range(iters):
+            par = k & 1
+            gg, dd = model.sweep(G, tiles, sl.r[par], sl.p[par], sl.x, sl.r[par ^ 1], sl.p[par ^ 1], alpha, beta, alpha_prev,
+                                 x2=bool(k & 1), slab=sl)
+            exchange(par ^ 1)
+            sums = torch.tensor([gg, dd], dtype=torch.float64)
+            dist.all_reduce(sums)
+            g2, d2 = float(sums[0]), float(sums[1])
+            alpha_prev = alpha if not (k & 1) else 0.0
+            beta = g2 / gamma
+            alpha, gamma = g2 / (d2 - beta * g2 / alpha), g2
+        x_own = sl.x + (alpha_prev * sl.p[iters & 1] if iters & 1 else 0.0)
+        parts = [None] * world
+        dist.all_gather_object(parts, (ylo, yhi, x_own[1:1 + yhi - ylo]))
+        if rank == 0:
+            xg = np.zeros((n + 1, G.pitch))
+            for a, c, rows in parts:
+                xg[a:c] = rows
+            # global single-reduction CG
+            r = b.copy(); p = np.zeros_like(b); xs = np.zeros_like(b)
+            ga = float(np.sum(r * r)); al = ga / float(np.sum(r * G.apply(r))); be = 0.0
+            for _ in range(iters):
+                p = r + be * p
+                xs = xs + al * p
+                r = r - al * G.apply(p)
+                g2 = float(np.sum(r * r)); d2 = float(np.sum(r * G.apply(r)))
+                be = g2 / ga
+                al, ga = g2 / (d2 - be * g2 / al), g2
+            assert np.max(np.abs(G.from_pitched(xg) - xs)) <= 1e-12 * np.max(np.abs(xs))
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,iters", [(64, 5), (96, 4)])
+def test_two_rank_single_sweep_protocol(tmp_path, n, iters):
+    import torch.multiprocessing as mp
+
+    from iterative_solvers_b200 import build
+
+    build.build_library()
+    port = _free_port()
+    mp.spawn(_single_sweep_worker, args=(2, port, n, iters, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
