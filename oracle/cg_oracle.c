@@ -237,6 +237,44 @@ void cgo_mf_solve(const cgo_grid* g, const double* b, const double* u, double ep
   info->seconds = now_s() - t0;
 }
 
+/* NOT a reference function: the same solve with alpha from the single-reduction CG recurrence (Chronopoulos-Gear),
+ *   gamma = r.r, delta = r.Ar, beta = gamma / gamma_prev, alpha = gamma / (delta - beta gamma / alpha_prev),
+ * in the reference's arithmetic (apply order, sequential dots, separately rounded updates). It is the CPU statement of
+ * what the product's opt-in single-sweep iteration computes (csrc/fused_kernel.cuh); tests compare it with
+ * cgo_mf_solve to show that the two stay at rounding distance. */
+void cgo_mf_solve_single(const cgo_grid* g, const double* b, double eps, int max_it, double* x, cgo_mf_info* info) {
+  long n = cgo_size(g);
+  double t0 = now_s();
+  double* r = (double*)malloc(sizeof(double) * n);
+  double* p = (double*)malloc(sizeof(double) * n);
+  double* Ap = (double*)malloc(sizeof(double) * n);
+  double* Ar = (double*)malloc(sizeof(double) * n);
+  for (long i = 0; i < n; ++i) { x[i] = 0.0; r[i] = b[i]; p[i] = 0.0; }
+  double gamma = dot(n, r, r);
+  double r_norm = sqrt(gamma), initial_r_norm = r_norm;
+  cgo_apply(g, r, Ar);
+  double alpha = gamma / dot(n, r, Ar), beta = 0.0;
+  int iterations;
+  for (iterations = 0; iterations < max_it && r_norm > eps * initial_r_norm; ++iterations) {
+    for (long i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+    cgo_apply(g, p, Ap);
+    for (long i = 0; i < n; ++i) x[i] += alpha * p[i];
+    for (long i = 0; i < n; ++i) r[i] -= alpha * Ap[i];
+    cgo_apply(g, r, Ar);
+    double gamma_new = dot(n, r, r), delta = dot(n, r, Ar);
+    r_norm = sqrt(gamma_new);
+    beta = gamma_new / gamma;
+    alpha = gamma_new / (delta - beta * gamma_new / alpha);
+    gamma = gamma_new;
+  }
+  info->iterations = iterations;
+  info->converged = r_norm <= eps * initial_r_norm;
+  info->r0_norm = initial_r_norm;
+  info->r_norm = r_norm;
+  free(r); free(p); free(Ap); free(Ar);
+  info->seconds = now_s() - t0;
+}
+
 /* Neighbour list of an unknown in the reference's per-row order; returns the count (grid_system.cpp:192-218). */
 static int row_entries(const cgo_grid* g, long row, int* cols, double* vals) {
   int xi, yi, k = 0;

@@ -54,6 +54,10 @@ typedef struct {
 void cgo_mf_solve(const cgo_grid* g, const double* b, const double* u, double eps, int max_it, double* x,
                   cgo_mf_info* info, double* hist, int hist_cap, double* snapshot_r, double* snapshot_p);
 
+/* Not a reference function: MatrixFreeSolver::solve with alpha from the single-reduction CG recurrence, in the
+ * reference's arithmetic - the CPU statement of the product's opt-in single-sweep iteration. */
+void cgo_mf_solve_single(const cgo_grid* g, const double* b, double eps, int max_it, double* x, cgo_mf_info* info);
+
 /* 0 = reference summation order (default), 1 = long-double accumulation (diagnostic, see cg_oracle.c) */
 void cgo_set_dot_mode(int mode);
 

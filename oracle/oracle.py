@@ -136,6 +136,15 @@ class Oracle:
             out["r"], out["p"] = r, p
         return out
 
+    def mf_solve_single(self, b=None, eps=1e-6, max_it=10000):
+        """The same solve with alpha from the single-reduction CG recurrence (not a reference function; see cg_oracle.c)."""
+        b = self.rhs() if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.N)
+        info = MfInfo()
+        self.L.cgo_mf_solve_single(C.byref(self.g), _opt(b), C.c_double(eps), int(max_it), _opt(x), C.byref(info))
+        return dict(x=x, iterations=info.iterations, converged=bool(info.converged), r0_norm=info.r0_norm,
+                    r_norm=info.r_norm, seconds=info.seconds)
+
     def csr(self):
         nnz = int(self.L.cgo_csr_nnz(C.byref(self.g)))
         row_map = np.empty(self.N + 1, dtype=np.int32)
