@@ -358,6 +358,7 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, args.iters, args.domain, args.op), "grid_n": n, "unknowns": plan.N,
                    "unknowns_per_gpu": plan.N / world, "iterations_per_step": args.iters,
+                   "iteration": "single sweep (b200cg_params.single_sweep = 1)" if single_sweep else "two sweeps (default)",
                    "parallelism": (f"row-slab x{world}, " + ("NVLink peer-memory halo + reductions" if peer_exchange
                                                             else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "inputs_exceed_l2" if n_local * 8 > 200e6 else "inputs_fit_l2_no_flush",
