@@ -2,7 +2,7 @@
  * hot path of Ruslan361/iterative_solvers.
  *
  * The reference has no FFI: its boundary is the public C++ surface of the static library `dirichlet_solver`
- * (solver/CMakeLists.txt:65). The drop-in C++ classes in iterative_solvers_b200/include/ keep those
+ * (solver/CMakeLists.txt:65). The drop-in C++ classes in iterative_solvers_b200/dropin/ keep those
  * signatures and route their bodies through the entry points below; each entry point names the reference
  * interface it replaces (paths relative to the reference root). INTEGRATION.md shows the binding.
  *
@@ -103,12 +103,13 @@ typedef struct {
   int small_grid_path;     /* grids that fit the shared memory of one thread-block cluster (about 300^2) are solved by
                               a single cluster-resident kernel instead of the graph loop: 0 = automatic, 1 = never,
                               2 = require it (B200CG_ERR_UNSUPPORTED if the grid does not fit) */
-  int single_sweep;        /* matrix-free, RULE_REL_L2, no callback, unsharded plan: 1 = run each iteration as ONE sweep
-                              (40 instead of 56 bytes per unknown) by forming alpha from the single-reduction CG
-                              recurrence (Chronopoulos-Gear) instead of p.Ap - the same iterates in exact arithmetic,
-                              <= 4e-14 relative apart in fp64 on the reference's grids
-                              (tests/studies/single_reduction_cg.py). 0 = the plan's default (off unless
-                              B200CG_SINGLE_SWEEP=1), 2 = never. Ignored where it does not apply */
+  int single_sweep;        /* matrix-free, RULE_REL_L2, no callback: each iteration runs as ONE sweep (40 instead of 56 bytes
+                              per unknown) by forming alpha from the single-reduction CG recurrence (Chronopoulos-Gear)
+                              instead of p.Ap - the same iterates in exact arithmetic, <= 4e-14 relative apart in fp64 on
+                              the reference's grids (tests/studies/single_reduction_cg.py), same iteration counts. On
+                              sharded plans it needs the peer-memory exchange and >= 4 rows per rank. 0 = the plan's
+                              default (on unless B200CG_SINGLE_SWEEP=0), 1 = on, 2 = never (the two-sweep iteration with
+                              alpha = r.r / p.Ap). Ignored where it does not apply */
   int reserved[5];
 } b200cg_params;
 
@@ -120,7 +121,8 @@ typedef struct {
   /* the three max-norms feed the MAXNORM stop rules; under B200CG_RULE_REL_L2 r_max and dx_max may be left 0 */
   double r_max;            /* ||r||_inf (recurrence) - MSGSolver::getFinalResidualNorm */
   double dx_max;           /* ||x_n - x_{n-1}||_inf  - MSGSolver::getFinalPrecision */
-  double err_max;          /* ||x - u||_inf          - MSGSolver::getFinalErrorNorm (DBL_MAX without u) */
+  double err_max;          /* ||x - u||_inf          - MSGSolver::getFinalErrorNorm (DBL_MAX without u, and under
+                              B200CG_RULE_REL_L2 without a callback, where nothing tracks it) */
   double total_ms;         /* host wall time of the whole call, copies included */
   double solve_ms;         /* device time of the iterations (CUDA events on the solve stream) */
   double device_ms;        /* device time of the whole call on the solve stream: H2D, init, iterations, D2H */
@@ -174,8 +176,8 @@ int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_hi, int64_t
  * unknowns x in [max(col0, xlo), min(col0 + 503, n - 1)]. CTA c walks tiles [cta_begin[c], cta_begin[c + 1]).
  * weights (n_weights entries, or NULL for the initial equal split) are the per-CTA shares feedback balancing
  * converges to. tiles holds `capacity` quadruples, cta_begin sms * ctas_per_sm + 1 ints. desc->reserved0 = 1 asks
- * for the single-sweep kernel's strips instead: 484 staged columns from storage column col0 = strip * 480 + 2, writing
- * x in [max(col0 - 2, xlo), min(col0 + 477, n - 1)]. */
+ * for the single-sweep kernel's strips instead: 424 staged columns from storage column col0 = strip * 420 + 2, writing
+ * x in [max(col0 - 2, xlo), min(col0 + 417, n - 1)]. */
 int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas_per_sm, const double* weights, int n_weights,
                       int* tiles, int64_t capacity, int64_t* n_tiles, int* cta_begin, int* grid);
 
@@ -206,8 +208,11 @@ int b200cg_csr_apply(b200cg_plan_t plan, const double* x_host, double* y_host);
 /* ------------------------------------------------------------------ solve
  * replaces MatrixFreeSolver::solve (matrix_free_system.cpp:383-482) and MSGSolver::solve (msg_solver.cpp:10-212).
  * b_host: rhs (ignored when params->rhs_on_device); u_host: true solution or NULL (empty true_solution);
- * x_host: receives the solution; stop_flag: polled between graph launches, non-zero -> INTERRUPTED
- * (MSGSolver::requestStop, msg_solver.hpp:76). */
+ * x_host: receives the solution; stop_flag: non-zero -> the solve ends with INTERRUPTED (MSGSolver::requestStop,
+ * msg_solver.hpp:76; the reference polls every iteration, msg_solver.cpp:82): the loop kernels look at the flag every
+ * 16th iteration (one kernel covers the whole solve on the small-grid path: every 128th). On a sharded plan raising it
+ * on ONE rank is enough: the request travels with the per-iteration reductions and every rank stops at the same
+ * iteration. params (max_it, iters_per_graph, rule, eps) must be identical on all ranks of a sharded plan. */
 int b200cg_solve(b200cg_plan_t plan, const b200cg_params* params, const double* b_host, const double* u_host,
                  double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user, const volatile int* stop_flag);
 

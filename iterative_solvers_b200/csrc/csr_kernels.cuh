@@ -43,6 +43,7 @@ struct CsrArgs {
   DevState* st;
   double* partials;
   CbRecord* cb_log;
+  const int* stop_flag;  // mapped host flag (requestStop), see poll_stop; null outside the solve loop
 };
 
 static inline CsrArgs csr_args(CsrData* c, DevState* st, double* partials, CbRecord* log, int par) {
@@ -61,6 +62,7 @@ static inline CsrArgs csr_args(CsrData* c, DevState* st, double* partials, CbRec
   a.st = st;
   a.partials = partials;
   a.cb_log = log;
+  a.stop_flag = nullptr;
   return a;
 }
 
@@ -266,7 +268,9 @@ static __global__ void __launch_bounds__(CTA_THREADS) csr_update_kernel(const Cs
     if (WITH_U) mx[2] = fmax(mx[2], fabs(__dsub_rn(xn, a.u[i])));       // msg_solver.cpp:132-139
   }
   if (!grid_reduce<1, 3>(s, mx, a.partials, st, scratch)) return;
+  const bool stop_req = poll_stop(st, a.stop_flag);
   finalize_update(st, a.cb_log, s[0], mx[0], mx[1], WITH_U ? mx[2] : DBL_MAX, 0.0, 0.0, false);
+  apply_stop(st, stop_req);
 }
 
 // Az <- A x - b (dirichlet_solver.cpp:147-161)

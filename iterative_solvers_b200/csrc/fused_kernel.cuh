@@ -11,46 +11,45 @@
 // of two rows / two columns and recomputes p and r' there. Element-wise arithmetic is unchanged (separately rounded
 // multiply/add in the reference's order, matrix_free_system.cpp:216-266, :422-438); only the way alpha is formed
 // differs, and tests/studies/single_reduction_cg.py shows the iterates stay within 4e-14 of the reference's on every
-// golden grid (same iteration counts). Opt-in (b200cg_params.single_sweep / B200CG_SINGLE_SWEEP), REL_L2 rule,
-// unsharded plans.
+// golden grid (same iteration counts). The default iteration of the REL_L2 rule without a report callback, on single
+// and on sharded (peer-memory) plans; b200cg_params.single_sweep = 2 / B200CG_SINGLE_SWEEP=0 select the two-sweep one.
 //
 // Structure: the producer warp / mbarrier stage ring of stream_kernel.cuh. Consumers differ in the column mapping:
 // every warp owns a window of 64 staged columns and writes the inner 60, so all horizontal neighbours (two levels)
-// come from warp shuffles and no lane needs another warp's data: 8 warps x 60 = 480 written columns per strip of
-// 484 staged ones. Rows run through a two-deep register pipeline: when row y arrives, A p and r' of row y-1 and
-// A r' of row y-2 become computable.
+// come from warp shuffles and no lane needs another warp's data. A CTA is 7 consumer warps + the producer = 8 warps:
+// at 2 CTAs/SM that leaves 128 registers per thread (a 9-warp CTA is capped at 96 and the x-touching flavour spilled,
+// profiles/r2_single_sweep.md), 7 x 60 = 420 written columns per strip of 424 staged ones. Rows run through a two-deep
+// register pipeline: when row y arrives, A p and r' of row y-1 and A r' of row y-2 become computable.
 #pragma once
 #include "stream_kernel.cuh"
 
 namespace b200cg {
 
-constexpr int FUSED_WARP_STEP = 60;     // columns written per consumer warp (64 processed)
-constexpr int FUSED_COL_SHIFT = 2;      // a strip's first staged storage column is strip * (columns written) + this
-constexpr int FUSED_STRIP_OUT = FUSED_WARP_STEP * CONS_WARPS;  // 480 columns written per strip (8 consumer warps)
-// CW consumer warps (template parameter, default 8; 7 is a tuning variant: an 8-warp CTA may use 128 registers)
-constexpr int fused_strip_out(int cw) { return FUSED_WARP_STEP * cw; }  // (host side: plan.cu)
+constexpr int FUSED_CW = 7;                                  // consumer warps per CTA
+constexpr int FUSED_THREADS = (FUSED_CW + 1) * 32;           // + the producer warp
+constexpr int FUSED_WARP_STEP = 60;                          // columns written per consumer warp (64 processed)
+constexpr int FUSED_COL_SHIFT = 2;                           // a strip's first staged storage column is strip * 420 + this
+constexpr int FUSED_STRIP_OUT = FUSED_WARP_STEP * FUSED_CW;  // 420 columns written per strip
+constexpr int FUSED_STRIP_COLS = FUSED_STRIP_OUT + 4;        // 424 staged columns: two halo columns per side
+constexpr int FUSED_ROW = FUSED_STRIP_COLS;                  // doubles between staged rows in shared memory (3392 B)
 
 template <int FLAGS>
 struct FusedCfg {
   static constexpr bool X2 = (FLAGS & F_X2) != 0;   // odd iteration: x += alpha_prev * p_old + alpha * p
   static constexpr bool NOX = !X2;                  // even iteration: x untouched, its update stays pending
   static constexpr int NSTREAM = X2 ? 3 : 2;        // p, r, [x]
-  // F_EDGE (tuning variant, B200CG_FUSED_DELTA=1): A is symmetric with a constant diagonal, so
-  //   r'.A r' = A_diag * sum r'^2 + 2 xk * sum_{horizontal edges} r'_i r'_j + 2 yk * sum_{vertical edges} r'_i r'_j ;
-  // every node owns the edge to its right and the edge above it. No second stencil, one halo row less below.
-  static constexpr bool EDGE = (FLAGS & F_EDGE) != 0;
-  static constexpr int NS = EDGE ? 3 : 2;           // gamma', delta'  |  gamma', horizontal, vertical edge sums
-  static constexpr int ROWS_BELOW = EDGE ? 1 : 2;   // rows streamed below a tile's first emit row
-  // F_SHARD (sharded plans, peer memory; B200CG_SINGLE_SWEEP_SHARDED=1, not yet run on hardware): the slab's two
-  // first / last rows of r' and p also go to the neighbours - into their halo row and into one of the two extra rows
-  // every pitched vector carries behind its stored rows (row ylo-2 at index yrows, row yhi+1 at index yrows+1) - and
-  // the iteration's two sums cross the ranks through the PeerSync slots, alternating the slot by iteration parity.
+  static constexpr int NS = 2;                      // gamma' = r'.r', delta' = r'.A r'
+  static constexpr int ROWS_BELOW = 2;              // rows streamed below a tile's first emit row
+  // F_SHARD (sharded plans, peer memory): the slab's two first / last rows of r' and p also go to the neighbours - into
+  // their halo row and into one of the two extra rows every pitched vector carries behind its stored rows (row ylo-2 at
+  // index yrows, row yhi+1 at index yrows+1) - and the iteration's two sums cross the ranks through the PeerSync slots,
+  // alternating the slot by iteration parity: ONE publish-and-wait per iteration.
   static constexpr bool SHARD = (FLAGS & F_SHARD) != 0;
 };
 
 template <int FLAGS, int HS, int NST>
 constexpr size_t fused_smem_bytes() {
-  return (size_t)NST * HS * FusedCfg<FLAGS>::NSTREAM * ROW_BYTES + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
+  return (size_t)NST * HS * FusedCfg<FLAGS>::NSTREAM * FUSED_ROW * 8 + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
 }
 
 // The scalars of the next iteration from gamma' = r'.r' and delta' = r'.A r' (one thread, after the grid reduction).
@@ -79,13 +78,13 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
   st->pAp = gamma_new / alpha;
 }
 
-template <int FLAGS, int HS, int NST, int CTAS, int CW = CONS_WARPS>
-__global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const TileArgs a) {
+template <int FLAGS, int HS, int NST>
+__global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileArgs a) {
   using Cfg = FusedCfg<FLAGS>;
-  constexpr bool X2 = Cfg::X2, EDGE = Cfg::EDGE, SHARD = Cfg::SHARD;
-  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
-  constexpr int STAGE_DOUBLES = HS * NSTREAM * STRIP_LOAD;
-  constexpr int OFF_P = 0, OFF_R = HS * STRIP_LOAD, OFF_X = 2 * HS * STRIP_LOAD;
+  constexpr bool X2 = Cfg::X2, SHARD = Cfg::SHARD;
+  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW, CW = FUSED_CW;
+  constexpr int STAGE_DOUBLES = HS * NSTREAM * FUSED_ROW;
+  constexpr int OFF_P = 0, OFF_R = HS * FUSED_ROW, OFF_X = 2 * HS * FUSED_ROW;
 
   const Geom& g = a.g;
   DevState* st = a.st;
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
   }
   __syncthreads();
 
-  double acc_s[NS] = {0.0};  // gamma', delta'  (F_EDGE: gamma', horizontal and vertical edge sums)
+  double acc_s[NS] = {0.0};  // gamma', delta'
   double acc_m[1] = {0.0};
   bool sent_halo = false;  // F_SHARD: this thread stored into a neighbour rank's rows
   const int y_store_lo = g.ybase, y_store_hi = g.ybase + g.yrows;  // stored rows [lo, hi)
@@ -131,9 +130,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
       for (int t = a.cta_begin[blockIdx.x]; t < t_end; ++t) {
         const Tile tl = a.tiles[t];
         const int col0 = tl.col0, ya = tl.ya, yb = tl.yb;
-        constexpr int STRIP_COLS = FUSED_WARP_STEP * CW + 4;  // staged columns: two halo columns per side
-        const uint32_t row_bytes = (uint32_t)min(STRIP_COLS, g.pitch - col0) * 8u;
-        const int S = yb - ya + 2 + LO;  // rows ya-2 .. yb+1 (F_EDGE: ya-1 .. yb+1)
+        const uint32_t row_bytes = (uint32_t)min(FUSED_STRIP_COLS, g.pitch - col0) * 8u;
+        const int S = yb - ya + 2 + LO;  // rows ya-2 .. yb+1
         for (int s0 = 0; s0 < S; s0 += HS) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const int nrows = min(HS, S - s0);
@@ -158,9 +156,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
             const int ri = row_index(y);
             if (ri < 0) continue;
             const size_t off = (size_t)ri * pitch + (size_t)col0;
-            bulk_g2s(sd + OFF_P + j * STRIP_LOAD, a.p_in + off, row_bytes, &full[stage]);
-            bulk_g2s(sd + OFF_R + j * STRIP_LOAD, a.r_in + off, row_bytes, &full[stage]);
-            if (X2 && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * STRIP_LOAD, a.x + off, row_bytes, &full[stage]);
+            bulk_g2s(sd + OFF_P + j * FUSED_ROW, a.p_in + off, row_bytes, &full[stage]);
+            bulk_g2s(sd + OFF_R + j * FUSED_ROW, a.r_in + off, row_bytes, &full[stage]);
+            if (X2 && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * FUSED_ROW, a.x + off, row_bytes, &full[stage]);
           }
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
@@ -223,7 +221,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
       // One staged row. full_tag: every row of the stage lies in [ya+2, yb), so it is stored, it is a row of the
-      // tile (masks va / vb), rows y-1 and y-2 are emit rows and x is staged: the per-row predicates fold away.
+      // tile, rows y-1 and y-2 are emit rows and x is staged: the per-row predicates fold away. There the staged inputs
+      // need no masks either: outside the unknowns r, p_old and x hold exact zeros in memory (so p = 0 + beta*0 is a
+      // zero too), and columns beyond the row pitch - stale shared memory - only ever feed results that are masked.
+      // Only r' must be masked, because A p does not vanish on boundary nodes.
       auto do_row = [&](const int j, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int y = m.y0 + j;
@@ -233,9 +234,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
         if (FULL) {
           k0a = va;
           k0b = vb;
-          cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * STRIP_LOAD + sc);
-          cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * STRIP_LOAD + sc);
-          if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + sc);
+          cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
+          cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
+          if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
         } else {
           const bool row_stored = row_index(y) >= 0;
           const bool row_ok = (y >= 1) && (y <= g.m - 1);
@@ -243,14 +244,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
           k0a = row_ok && (x0 >= xlo) && (x0 <= g.n - 1);
           k0b = row_ok && (x0 + 1 >= xlo) && (x0 + 1 <= g.n - 1);
           if (row_stored) {
-            cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * STRIP_LOAD + sc);
-            cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * STRIP_LOAD + sc);
-            if (X2 && y >= ya && y < yb) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * STRIP_LOAD + sc);
+            cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
+            cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
+            if (X2 && y >= ya && y < yb) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
           }
+          cur_p.x = k0a ? cur_p.x : 0.0;  cur_p.y = k0b ? cur_p.y : 0.0;
+          cur_r.x = k0a ? cur_r.x : 0.0;  cur_r.y = k0b ? cur_r.y : 0.0;
+          cur_x.x = k0a ? cur_x.x : 0.0;  cur_x.y = k0b ? cur_x.y : 0.0;
         }
-        cur_p.x = k0a ? cur_p.x : 0.0;  cur_p.y = k0b ? cur_p.y : 0.0;
-        cur_r.x = k0a ? cur_r.x : 0.0;  cur_r.y = k0b ? cur_r.y : 0.0;
-        cur_x.x = k0a ? cur_x.x : 0.0;  cur_x.y = k0b ? cur_x.y : 0.0;
         double2 P0;
         P0.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
         P0.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
@@ -300,29 +301,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
           acc_s[0] = fma(R0.y, R0.y, acc_s[0]);
         }
         const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
+        const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
+        // ---- row y-2: A r' and delta' += r'.A r'
         const bool emit2 = FULL || ((y - 2 >= ya) && (y - 2 < yb));
-        if (EDGE) {
-          // edges owned by the nodes of row y-1 (to the right) and of row y-2 (upwards, to row y-1)
-          if (emit1 && writer) {
-            acc_s[1] = fma(R0.x, R0.y, acc_s[1]);
-            acc_s[1] = fma(R0.y, RR0, acc_s[1]);
-          }
-          if (emit2 && writer) {
-            acc_s[NS - 1] = fma(R1.x, R0.x, acc_s[NS - 1]);
-            acc_s[NS - 1] = fma(R1.y, R0.y, acc_s[NS - 1]);
-          }
-          R1 = R0;
-        } else {
-          const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
-          // ---- row y-2: A r' and delta' += r'.A r'
-          if (emit2 && writer) {
-            const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
-            const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
-            acc_s[1] = fma(R1.x, w0, acc_s[1]);
-            acc_s[1] = fma(R1.y, w1, acc_s[1]);
-          }
-          R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
+        if (emit2 && writer) {
+          const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
+          const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
+          acc_s[1] = fma(R1.x, w0, acc_s[1]);
+          acc_s[1] = fma(R1.y, w1, acc_s[1]);
         }
+        R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
 
         // ---- shift the pipeline
         P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
@@ -346,19 +334,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, CTAS) cg_fused_kernel(const Til
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
   if (SHARD && sent_halo) __threadfence_system();  // remote halo stores before the exit ticket
   if (!grid_reduce<NS, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
+  bool stop_req = poll_stop(st, a.stop_flag);
   double gamma = acc_s[0];
-  double delta = EDGE ? g.A * acc_s[0] + 2.0 * g.xk * acc_s[1] + 2.0 * g.yk * acc_s[NS - 1] : acc_s[1];  // (linear in the sums)
+  double delta = acc_s[1];
   if (SHARD) {
     // this rank's two sums to every rank, everyone's back; the slot alternates with the iteration parity so that a fast
     // rank's next publication cannot overwrite values a slow rank is still reading
     const int phase = X2 ? 1 : 0;
     double mine[2] = {gamma, delta}, none[1] = {0.0}, total[4];
-    peer_publish<2, 0>(a.peers, st, phase, mine, none);
-    if (!peer_collect(st, a.peers, phase, total)) return;
+    peer_publish<2, 0>(a.peers, st, phase, mine, none, stop_req);
+    if (!peer_collect(st, a.peers, phase, total, &stop_req)) return;
     gamma = total[0];
     delta = total[1];
   }
   finalize_fused(st, gamma, delta, FLAGS);
+  apply_stop(st, stop_req);
 }
 
 }  // namespace b200cg

@@ -24,7 +24,6 @@ enum {
   F_SUB_B = 4,   // APPLY: out = A v - b
   F_NOX = 8,     // UPD, x-deferral: even iteration, x is not touched (its update stays pending)
   F_X2 = 16,     // UPD, x-deferral: odd iteration, applies the pending update and this one
-  F_EDGE = 32,   // single-sweep kernel: r'.A r' from edge sums instead of a second stencil (fused_kernel.cuh)
   F_SHARD = 64   // single-sweep kernel on a sharded plan: two halo rows per side over peer memory
 };
 
@@ -55,6 +54,7 @@ struct TileArgs {
   double* nb_r_above2;
   double* nb_p_above2;
   unsigned long long* cta_clock;  // [2 * gridDim.x] globaltimer at CTA start / end of its sweep (load balancing)
+  const int* stop_flag;  // mapped host flag (requestStop, msg_solver.cpp:82), polled every STOP_POLL_EVERY-th iteration
   Geom g;
 };
 
@@ -166,6 +166,23 @@ __device__ __forceinline__ void append_record(DevState* st, CbRecord* log, doubl
   st->n_log = k + 1;
 }
 
+// requestStop (msg_solver.cpp:82 polls its flag every iteration): the thread that forms the scalars looks at the host's
+// mapped flag every STOP_POLL_EVERY-th iteration (a read over PCIe costs ~2 us), so a stop lands within that many
+// iterations instead of at the next graph boundary. Call before st->it is advanced; on a sharded plan every rank
+// looks at the same iterations and the maximum over the ranks decides, so all ranks stop together.
+constexpr int STOP_POLL_EVERY = 16;
+__device__ __forceinline__ bool poll_stop(const DevState* st, const int* stop_flag) {
+  if (!stop_flag || ((st->it + 1) % STOP_POLL_EVERY) != 0) return false;
+  return *reinterpret_cast<const volatile int*>(stop_flag) != 0;
+}
+__device__ __forceinline__ void apply_stop(DevState* st, bool stop_req) {
+  if (stop_req && !st->done) {  // (a stop rule that fired in the same iteration wins)
+    st->done = 1;
+    st->converged = 0;
+    st->stop_reason = 4;  // B200CG_STOP_INTERRUPTED
+  }
+}
+
 // alpha = r.r / p.Ap (matrix_free_system.cpp:417-419) or r.z / Az.z (msg_solver.cpp:96-102)
 __device__ __forceinline__ void finalize_dot(DevState* st, double pAp, double rz) {
   st->pAp = pAp;
@@ -185,14 +202,16 @@ __device__ __forceinline__ void finalize_report(DevState* st, CbRecord* log, dou
 // system-scope fence - the epoch flag, into every rank's PeerSync block.
 template <int NS, int NM>
 __device__ __forceinline__ void peer_publish(const PeerLinks* pl, DevState* st, int phase, const double (&s)[NS > 0 ? NS : 1],
-                                             const double (&mx)[NM > 0 ? NM : 1]) {
+                                             const double (&mx)[NM > 0 ? NM : 1], bool stop_req = false) {
+  static_assert(NM <= 3, "max slot 3 carries the stop request");
   const unsigned long long epoch = st->epoch[phase] + 1ull;
   for (int dst = 0; dst < pl->world; ++dst) {
     double* v = pl->sync[dst]->vals[phase][pl->rank];
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = k < NS ? s[k < NS ? k : 0] : 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[4 + k] = k < NM ? mx[k < NM ? k : 0] : 0.0;
+    for (int k = 0; k < 3; ++k) v[4 + k] = k < NM ? mx[k < NM ? k : 0] : 0.0;
+    v[7] = stop_req ? 1.0 : 0.0;
   }
   __threadfence_system();
   for (int dst = 0; dst < pl->world; ++dst)
@@ -296,12 +315,13 @@ __device__ __forceinline__ void peer_finalize(DevState* st, CbRecord* log, const
     finalize_update(st, log, s[0], mx[0], mx[1], has_u ? mx[2] : DBL_MAX, report ? s[1] : 0.0,
                     (report && has_u) ? s[2] : 0.0, report);
     note_x_deferral(st, flags);
+    apply_stop(st, mx[3] > 0.0);
   }
 }
 
 // The wait half of peer_finalize alone (single-sweep kernel): true when every rank's publication of this epoch of
 // `phase` has landed; the summed slots come back in s[0..3]. On a timeout the solve is ended with comm_error.
-__device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, int phase, double (&s)[4]) {
+__device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, int phase, double (&s)[4], bool* stop_req) {
   const unsigned long long epoch = st->epoch[phase] + 1ull;
   const PeerSync* mine = pl->sync[pl->rank];
   bool ok = true;
@@ -324,11 +344,14 @@ __device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, 
     return false;
   }
   s[0] = s[1] = s[2] = s[3] = 0.0;
+  double stop = 0.0;
   for (int r = 0; r < pl->world; ++r) {
     const volatile double* v = mine->vals[phase][r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) s[k] += v[k];
+    stop = fmax(stop, v[7]);
   }
+  *stop_req = stop > 0.0;
   return true;
 }
 

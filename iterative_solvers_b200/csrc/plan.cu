@@ -226,7 +226,22 @@ int b200cg::rebalance_tiles(b200cg_plan_s* P, int flavour) {
     wsum += tt->weight[c];
   }
   for (double& w : tt->weight) w *= tt->grid / wsum;
+  // consumed: a later solve that does not launch this flavour must not re-apply these stamps
+  CU(cudaMemset(P->d_clock[flavour], 0, clk.size() * sizeof(unsigned long long)));
   return upload_tiles(P, tt);
+}
+
+// Cached graphs hold the device pointers of the buffers they were captured with: whoever frees such buffers drops the
+// graphs that captured them.
+void b200cg::drop_graphs(b200cg_plan_s* P, int variant_mask) {
+  for (auto it = P->graphs.begin(); it != P->graphs.end();) {
+    if ((it->first / 4096) & variant_mask) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      it = P->graphs.erase(it);
+    } else {
+      ++it;
+    }
+  }
 }
 
 int b200cg::ew_grid(const b200cg_plan_s* P, long long work_items) {
@@ -433,14 +448,13 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_dot = env_int("B200CG_SHAPE_DOT", P->shape_dot);
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
-    P->shape_fused = env_int("B200CG_SHAPE_FUSED", P->shape_fused);
-    P->fused_edge_sums = env_int("B200CG_FUSED_DELTA", 0) != 0;
-    P->fused_sharded = env_int("B200CG_SINGLE_SWEEP_SHARDED", 0) != 0;
+    P->shape_fused_nox = env_int("B200CG_FUSED_NOX", P->shape_fused_nox);
+    P->shape_fused_x2 = env_int("B200CG_FUSED_X2", P->shape_fused_x2);
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->balance_rounds_fused = P->balance_rounds;
     P->cluster_enabled = env_int("B200CG_CLUSTER", 1) != 0;
-    P->single_sweep_default = env_int("B200CG_SINGLE_SWEEP", 0) != 0;
+    P->single_sweep_default = env_int("B200CG_SINGLE_SWEEP", 1) != 0;
     if (!P->generic && P->cluster_enabled) {
       // probe once whether the non-portable 16-CTA cluster is schedulable with a full shared-memory carve-out
       cudaLaunchConfig_t cfg = {};
@@ -469,7 +483,7 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->tile_tab[1].ctas_per_sm = ctas_of(P->shape_nox);
     P->tile_tab[2].ctas_per_sm = 2;  // every other flavour runs a 2-CTAs/SM shape
     P->tile_tab[3].ctas_per_sm = 2;  // single-sweep iteration: its own strip geometry (fused_kernel.cuh)
-    P->tile_tab[3].strip_out = P->shape_fused == 2 ? fused_strip_out(7) : FUSED_STRIP_OUT;
+    P->tile_tab[3].strip_out = FUSED_STRIP_OUT;
     P->tile_tab[3].col_shift = FUSED_COL_SHIFT;
     if (P->shape_upd == 1) P->shape_upd = 0;
     for (auto& tt : P->tile_tab) RET(upload_tiles(P, &tt));
@@ -547,8 +561,8 @@ extern "C" int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas
   tmp.sms = sms;
   TileTable tt;
   tt.ctas_per_sm = ctas_per_sm;
-  if (desc->reserved0 == 1 || desc->reserved0 == 2) {  // the single-sweep kernel's strip geometry (2: 7 consumer warps)
-    tt.strip_out = desc->reserved0 == 2 ? fused_strip_out(7) : FUSED_STRIP_OUT;
+  if (desc->reserved0 == 1) {  // the single-sweep kernel's strip geometry
+    tt.strip_out = FUSED_STRIP_OUT;
     tt.col_shift = FUSED_COL_SHIFT;
   }
   if (weights && n_weights > 0) tt.weight.assign(weights, weights + n_weights);
@@ -674,6 +688,8 @@ extern "C" int b200cg_set_csr(b200cg_plan_t P, int64_t nrows, int64_t nnz, const
   if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
   if (nrows != P->n_global) return fail(B200CG_ERR_INVALID_ARG, "nrows %lld != unknowns %lld", (long long)nrows, (long long)P->n_global);
   CU(cudaSetDevice(P->desc.device));
+  drop_graphs(P, V_CSR);  // they captured the buffers csr_upload frees
+  if (P->solution_in_csr) P->have_solution = P->solution_in_csr = false;  // the solution lived in the freed vectors
   std::string err;
   int rc = csr_upload(&P->csr, nrows, nnz, row_map, entries, values, P->stream, &err);
   if (rc) return fail(rc, "%s", err.c_str());
@@ -684,6 +700,8 @@ extern "C" int b200cg_assemble_csr(b200cg_plan_t P, int64_t* nnz) {
   NEED_GEOMETRY(P);
   if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
   CU(cudaSetDevice(P->desc.device));
+  drop_graphs(P, V_CSR);  // they captured the buffers csr_assemble frees
+  if (P->solution_in_csr) P->have_solution = P->solution_in_csr = false;  // the solution lived in the freed vectors
   std::string err;
   int rc = csr_assemble(&P->csr, P->g, P->n_global, P->sms, P->stream, &err);
   if (rc) return fail(rc, "%s", err.c_str());

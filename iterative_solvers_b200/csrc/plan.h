@@ -51,6 +51,9 @@ namespace b200cg {
 double now_ms();
 
 // ------------------------------------------------------------------------------------------- plan
+// Graph variants (key of b200cg_plan_s::graphs = variant * 4096 + iterations per graph)
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16 };
+
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   int iters = 0;
@@ -80,14 +83,11 @@ struct b200cg_plan_s {
   TileTable tile_tab[4];  // sweep work lists per flavour
   int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int balance_rounds_fused = 0;  // the same for the single-sweep flavour, counted from its own first launches
-  int shape_fused = 0;                              // single-sweep kernel: 0 = 4-row stages, 1 = 3-row stages, 2 = 7 consumer warps
-  bool fused_sharded = false;                       // single-sweep iteration on sharded plans (B200CG_SINGLE_SWEEP_SHARDED=1;
-                                                    // written against the CPU model only, not yet run on hardware)
-  bool fused_edge_sums = false;                     // single-sweep kernel: r'.A r' from edge sums (B200CG_FUSED_DELTA=1)
+  int shape_fused_nox = 0, shape_fused_x2 = 0;      // single-sweep kernel: stage shapes of the even / odd flavour (launch_fused_flags)
   int shape_dot = 3, shape_upd = 2, shape_nox = 2;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   bool cluster_enabled = true;                      // small-grid path allowed (B200CG_CLUSTER=0 disables)
-  bool single_sweep_default = false;                // B200CG_SINGLE_SWEEP=1: single-sweep iteration unless a solve says no
+  bool single_sweep_default = true;                 // single-sweep iteration wherever it applies (B200CG_SINGLE_SWEEP=0: two sweeps)
   bool cluster16_ok = false;                        // a 16-CTA cluster of the small-grid kernel can be scheduled
   cudaStream_t stream = nullptr;
   size_t vec_elems = 0;  // doubles per pitched vector
@@ -109,7 +109,7 @@ struct b200cg_plan_s {
   int* d_stop = nullptr;
   double* d_partials = nullptr;
   int partial_slots = 0;
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[11] = {};
   bool have_rhs = false, have_u = false, have_solution = false;
   bool generic = false;          // B200CG_DOMAIN_GENERIC: CSR entry points only, no pitched vectors
   bool solution_in_csr = false;  // the last solve ran on the assembled path
@@ -142,5 +142,6 @@ int ensure_scratch(b200cg_plan_s* P);
 int exchange_halo(b200cg_plan_s* P, double* v);                  // one-row halo over NCCL (no-op on one GPU)
 int exchange_halo2(b200cg_plan_s* P, double* v0, double* v1);
 int rebalance_tiles(b200cg_plan_s* P, int flavour);              // one feedback step of the work split
+void drop_graphs(b200cg_plan_s* P, int variant_mask);            // destroys the cached graphs whose variant has a bit of the mask
 
 }  // namespace b200cg

@@ -21,8 +21,6 @@ extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_hos
 }
 
 // ------------------------------------------------------------------------------------------- solve
-enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16 };
-
 // Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
 // read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
 static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
@@ -37,21 +35,21 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     if (k == 0) cudaEventRecordWithFlags(P->ev[0], s, cudaEventRecordExternal);
     if (csr) {
       // assembled path: p update + SpMV + dots, then the shared update pass
-      csr_spmv_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
-          csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+      CsrArgs ca = csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par);
+      ca.stop_flag = P->d_stop;
+      csr_spmv_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       ++kernels;
       if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
       if (with_u)
-        csr_update_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
-            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+        csr_update_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       else
-        csr_update_kernel<0><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(
-            csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par));
+        csr_update_kernel<0><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       ++kernels;
       if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
       continue;
     }
     TileArgs a = base_args(P);
+    a.stop_flag = P->d_stop;
     a.r_in = P->r[par];
     a.p_in = P->p[par];
     a.x = P->x;
@@ -301,6 +299,8 @@ static int arm_device_state(SolveCall& c) {
 static void deliver_callbacks(SolveCall& c) {
   const DevState& st = *c.P->h_state;
   if (c.cb) {
+    // (the launch sizes keep a launch's records within the ring; should one ever lap it, deliver the surviving tail only)
+    if (st.n_log - c.consumed > (unsigned int)CB_LOG_CAP) c.consumed = st.n_log - CB_LOG_CAP;
     for (; c.consumed < st.n_log; ++c.consumed) {
       const CbRecord& rec = c.P->h_log[c.consumed % CB_LOG_CAP];
       c.cb(c.user, (int)rec.it, rec.precision, rec.residual, rec.error);
@@ -416,10 +416,11 @@ static int run_graph_solve(SolveCall& c) {
   b200cg_plan_s* P = c.P;
   const b200cg_params* prm = c.prm;
   cudaStream_t s = P->stream;
-  // single-sweep iteration (opt-in): relative-residual rule without report on an unsharded plan
+  // single-sweep iteration (the default): relative-residual rule without report; sharded plans need the peer-memory
+  // exchange and at least 4 rows per rank (every rank sees all cuts, so all ranks decide alike)
   const bool want_fused = prm->single_sweep == 1 || (prm->single_sweep == 0 && P->single_sweep_default);
   bool fused_ok = P->desc.world <= 1;
-  if (!fused_ok && P->fused_sharded && P->peer_mode) {  // sharded: every rank must own >= 4 rows (all ranks see all cuts)
+  if (!fused_ok && P->peer_mode) {
     fused_ok = true;
     for (int r = 0; r < P->desc.world; ++r) fused_ok = fused_ok && (P->ycuts[r + 1] - P->ycuts[r] >= 4);
   }
@@ -428,7 +429,9 @@ static int run_graph_solve(SolveCall& c) {
   int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
   if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
   K = std::max(2, (K + 1) & ~1);
-  K = std::min(K, c.report ? CB_LOG_CAP / 2 : CB_LOG_CAP);
+  // callback records of one launch must fit the ring: report = one per iteration, MAXNORM with callback_every = 1 one per
+  // iteration plus the init record
+  K = std::min(K, c.report ? CB_LOG_CAP / 2 : (c.cb ? CB_LOG_CAP - 2 : CB_LOG_CAP));
   // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
   c.xdefer = c.fused || (P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2);
   const int variant = c.fused ? V_FUSED
@@ -438,10 +441,24 @@ static int run_graph_solve(SolveCall& c) {
 
   CU(cudaEventRecord(P->ev[5], s));
   int it_before = 0;
+  *P->h_stop = 0;
+  // Interrupts (requestStop): the caller's flag is forwarded into the mapped flag the loop kernels poll every
+  // STOP_POLL_EVERY-th iteration; the device then ends the solve with INTERRUPTED - on a sharded peer-memory plan on
+  // every rank at the same iteration (the request travels with the reduction slots). Only the NCCL exchange (fallback,
+  // per-iteration report) lacks that channel: there the ranks agree between graph launches.
+  const bool device_stop = P->desc.world <= 1 || (P->peer_mode && !c.report);
   // the init kernel's verdict (0 iterations) and its callback record come back with the first graph launch
   for (;;) {
+    if (c.stop_flag && *c.stop_flag) *P->h_stop = 1;
     CU(cudaGraphLaunch(ge.exec, s));
     c.info->kernel_launches += ge.kernels;
+    if (c.stop_flag) {
+      CU(cudaEventRecord(P->ev[10], s));
+      for (int spins = 0; cudaEventQuery(P->ev[10]) == cudaErrorNotReady; ++spins) {
+        if (*c.stop_flag) *P->h_stop = 1;
+        if (spins > 20000) std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
+    }
     CU(cudaStreamSynchronize(s));
     const DevState& st = *P->h_state;
     const int advanced = st.it - it_before;
@@ -460,11 +477,22 @@ static int run_graph_solve(SolveCall& c) {
       }
       --rounds;
     }
-    if (c.stop_flag && *c.stop_flag) {
+    bool stop = c.stop_flag && *c.stop_flag;
+    if (stop) *P->h_stop = 1;
+    if (!device_stop) {  // NCCL exchange: every rank learns whether any rank wants to stop (all ranks call this)
+      bool none = true;
+      std::string err;
+      if (!comm_all_agree(&P->comm, !stop, &none, s, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
+      stop = !none;
+    } else if (P->desc.world > 1) {
+      stop = false;  // the device verdict is the collective one
+    }
+    if (stop) {
       c.interrupted = true;
       break;
     }
   }
+  if (P->h_state->stop_reason == B200CG_STOP_INTERRUPTED) c.interrupted = true;
   return B200CG_OK;
 }
 
@@ -502,7 +530,8 @@ static void fill_info(const SolveCall& c, const DevState& st) {
   info->r_l2 = st.r_norm;
   info->r_max = st.r_max;
   info->dx_max = st.dx_max;
-  info->err_max = st.err_max;
+  // the x-deferral / single-sweep flavours (REL_L2 without callback) do not track |x - u|_inf: nothing reads it there
+  info->err_max = c.xdefer ? DBL_MAX : st.err_max;
   auto span = [&](int a, int b) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, P->ev[a], P->ev[b]);
@@ -547,7 +576,10 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   int cl_rows = 0, cl_ctas = 0;
   size_t cl_smem = 0;
   {
-    const long long cb_records = 2 + (long long)std::max(prm->max_it, 0) / 100;
+    // the single launch appends every record of the solve to the ring: it 0, it 1, every callback_every-th (the value
+    // arm_device_state hands the device), so a dense cadence or a long solve stays on the graph path
+    const int every = prm->callback_every > 0 ? prm->callback_every : 100;
+    const long long cb_records = 3 + (long long)std::max(prm->max_it, 0) / every;
     const bool eligible = !c.csr && !c.report && prm->small_grid_path != 1 && P->cluster_enabled && !(cb && cb_records > CB_LOG_CAP);
     if (eligible) cl_ctas = cluster_ctas_for(P, &cl_rows, &cl_smem);
     if (prm->small_grid_path == 2 && cl_ctas == 0)

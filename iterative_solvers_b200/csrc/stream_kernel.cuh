@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
   if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
   // ---- one thread: turn the totals into the next scalars
   if (a.defer == 2) {  // peer memory: publish this rank's totals to every rank, then collect everyone's
-    peer_publish<NS, NM>(a.peers, st, MODE == MODE_DOT ? 0 : 1, acc_s, acc_m);
+    peer_publish<NS, NM>(a.peers, st, MODE == MODE_DOT ? 0 : 1, acc_s, acc_m, MODE == MODE_UPD && poll_stop(st, a.stop_flag));
     peer_finalize(st, a.cb_log, a.peers, MODE == MODE_DOT ? 1 : 2, FLAGS);
     return;
   }
@@ -395,10 +395,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
   if (MODE == MODE_DOT) {
     finalize_dot(st, acc_s[0], acc_s[1]);
   } else if (MODE == MODE_UPD) {
+    const bool stop_req = poll_stop(st, a.stop_flag);
     finalize_update(st, a.cb_log, acc_s[0], NM > 0 ? acc_m[0] : 0.0, NM > 1 ? acc_m[NM > 1 ? 1 : 0] : 0.0,
                     LOAD_U ? acc_m[NM > 0 ? NM - 1 : 0] : DBL_MAX,
                     REPORT ? acc_s[1] : 0.0, (REPORT && LOAD_U) ? acc_s[2] : 0.0, REPORT);
     note_x_deferral(st, FLAGS);
+    apply_stop(st, stop_req);
   } else if (REPORT) {
     finalize_report(st, a.cb_log, acc_s[0], LOAD_U ? acc_s[1] : 0.0, LOAD_U);
   }

@@ -75,16 +75,12 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
   return launch_shape<MODE, FLAGS, 0>(P, a, s);
 }
 
-// The single-sweep iteration (fused_kernel.cuh), 2 CTAs/SM, ~96-108 KB of copy destinations per CTA.
-// Shape 0 (default): 4-row stages. Shape 1 (B200CG_SHAPE_FUSED=1, tuning knob): 3-row stages - the two register
-// pipelines of the row loop have period 3, so an unrolled 3-row stage needs no register rotation.
-template <int FLAGS, int SHAPE>
-static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
-  constexpr bool X2 = FusedCfg<FLAGS>::X2;
-  constexpr int HS = SHAPE == 1 ? 3 : 4, NST = SHAPE == 1 ? (X2 ? 3 : 4) : (X2 ? 2 : 3), CTAS = 2;
-  constexpr int CW = SHAPE == 2 ? 7 : CONS_WARPS;  // shape 2: 7 consumer warps = 8-warp CTAs (128-register budget)
-  auto kernel = cg_fused_kernel<FLAGS, HS, NST, CTAS, CW>;
+// The single-sweep iteration (fused_kernel.cuh): 8-warp CTAs, 2 CTAs/SM, 80-109 KB of copy destinations per CTA.
+template <int FLAGS, int HS, int NST>
+static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
+  auto kernel = cg_fused_kernel<FLAGS, HS, NST>;
   constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST>();
+  static_assert(smem + 1024 <= 114 * 1024, "two CTAs per SM");
   static thread_local bool configured[64] = {};
   const int dev = P->desc.device & 63;
   if (!configured[dev]) {
@@ -97,23 +93,32 @@ static int launch_fused_shape(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   a.cta_begin = tt.d_cta_begin;
   a.cta_clock = P->d_clock[3];
   P->clock_ctas[3] = tt.grid;
-  kernel<<<tt.grid, (CW + 1) * 32, smem, s>>>(a);
+  kernel<<<tt.grid, FUSED_THREADS, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
 }
+// Stage shapes (rows per stage x stages): even iterations stream r, p_old (27 KB per 4-row stage), odd ones also x
+// (41 KB). B200CG_FUSED_NOX / _X2 select the alternatives (tuning knobs, measured in profiles/r2_single_sweep.md).
+template <int FLAGS>
+static int launch_fused_flags(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
+  if constexpr ((FLAGS & F_X2) != 0) {
+    switch (P->shape_fused_x2) {
+      case 1: return launch_fused_cfg<FLAGS, 2, 5>(P, a, s);
+      case 2: return launch_fused_cfg<FLAGS, 3, 3>(P, a, s);
+      default: return launch_fused_cfg<FLAGS, 4, 2>(P, a, s);
+    }
+  } else {
+    switch (P->shape_fused_nox) {
+      case 1: return launch_fused_cfg<FLAGS, 4, 3>(P, a, s);
+      case 2: return launch_fused_cfg<FLAGS, 2, 8>(P, a, s);
+      default: return launch_fused_cfg<FLAGS, 4, 4>(P, a, s);
+    }
+  }
+}
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (a.defer == 2) {  // sharded plan, peer memory (default shape, stencil form only)
-    if (P->shape_fused == 2) return fail(B200CG_ERR_UNSUPPORTED, "B200CG_SHAPE_FUSED=2 has no sharded variant");
-    return launch_fused_shape<FLAGS | F_SHARD, 0>(P, a, s);
-  }
-  // the tile table of flavour 3 was cut for the shape's strip width when the plan was created (plan.cu)
-  if (P->fused_edge_sums) {  // B200CG_FUSED_DELTA=1 (tuning variant): r'.A r' from edge sums
-    if (P->shape_fused == 2) return launch_fused_shape<FLAGS | F_EDGE, 2>(P, a, s);
-    return P->shape_fused == 1 ? launch_fused_shape<FLAGS | F_EDGE, 1>(P, a, s) : launch_fused_shape<FLAGS | F_EDGE, 0>(P, a, s);
-  }
-  if (P->shape_fused == 2) return launch_fused_shape<FLAGS, 2>(P, a, s);
-  return P->shape_fused == 1 ? launch_fused_shape<FLAGS, 1>(P, a, s) : launch_fused_shape<FLAGS, 0>(P, a, s);
+  if (a.defer == 2) return launch_fused_flags<FLAGS | F_SHARD>(P, a, s);  // sharded plan, peer memory
+  return launch_fused_flags<FLAGS>(P, a, s);
 }
 
 static TileArgs base_args(b200cg_plan_s* P) {

@@ -1,6 +1,6 @@
-"""CPU model of the single-sweep kernel's data flow (csrc/fused_kernel.cuh), lane by lane: the 484/480-column strips,
-the 64-column warp windows with shuffle neighbours, the two-deep row pipeline, the per-row unknown masks and the
-rows a tile streams (ya-2 .. yb+1). It runs whole CG iterations on small grids from the real tile tables
+"""CPU model of the single-sweep kernel's data flow (csrc/fused_kernel.cuh), lane by lane: the 424/420-column strips,
+the 64-column warp windows with shuffle neighbours, the two-deep row pipeline, the per-row unknown masks (and their
+absence on the inputs of FULL stages) and the rows a tile streams (ya-2 .. yb+1). It runs whole CG iterations on small grids from the real tile tables
 (b200cg_work_split, no GPU) and compares them with a plain numpy single-reduction CG. Columns the bulk copies would
 leave stale in shared memory are NaN here, so a missing mask shows up at once.
 
@@ -14,7 +14,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from iterative_solvers_b200 import capi  # noqa: E402
 
-XOFF, STRIP_COLS, WARP_STEP, STRIP_LOAD = 4, 484, 60, 512
+XOFF, WARPS, WARP_STEP, STRIP_LOAD, HS = 4, 7, 60, 512, 4
 
 
 def shfl_up(v):
@@ -85,19 +85,20 @@ class Slab:
         return -1
 
 
-def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, edge=False, slab=None, nb_below=None,
-          nb_above=None, warps=8):
-    """One launch of the kernel over all tiles; returns (gamma', delta'). edge: the F_EDGE variant (r'.A r' from
-    edge sums, rows streamed from ya-1). slab / nb_*: the F_SHARD variant - this rank's Slab and the (r_out, p_out)
-    arrays of the neighbour ranks, whose halo rows receive this slab's two first / last rows."""
+def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, slab=None, nb_below=None,
+          nb_above=None, warps=WARPS):
+    """One launch of the kernel over all tiles; returns (gamma', delta'). slab / nb_*: the F_SHARD variant - this
+    rank's Slab and the (r_out, p_out) arrays of the neighbour ranks, whose halo rows receive this slab's two first /
+    last rows."""
+    shard = nb_below is not None or nb_above is not None or slab is not None
     if slab is None:
         slab = Slab(G, 1, G.m, False, False)  # one rank owning every row: rows 0 .. m stored, no extra rows in use
-    warp = np.arange(warps)[:, None]  # consumer warps (8, or 7 in the B200CG_SHAPE_FUSED=2 variant)
+    warp = np.arange(warps)[:, None]  # consumer warps
     lane = np.arange(32)[None, :]
     sc = WARP_STEP * warp + 2 * lane
     writer = (lane >= 1) & (lane <= 30) & (warp >= 0)
     strip_cols = WARP_STEP * warps + 4
-    gam = dlt = dh = dv = 0.0
+    gam = dlt = 0.0
 
     def stencil(c, l, r, t, b):
         v = G.A * c
@@ -115,7 +116,10 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
         R1x, R1y, R2x, R2y, LR1, RR1 = z, z, z, z, z, z
         r1x, r1y, x1x, x1y, q1x, q1y = z, z, z, z, z, z
         k1a = k1b = np.zeros((warps, 32), dtype=bool)
-        for y in range(ya - (1 if edge else 2), yb + 2):
+        for y in range(ya - 2, yb + 2):
+            # the stage this row arrives in (HS rows from ya-2 on) and whether the kernel takes its FULL path there
+            y0 = ya - 2 + (y - (ya - 2)) // HS * HS
+            full = y0 + HS <= yb + 2 and y0 >= ya + (3 if shard else 2) and y0 + HS <= yb - (1 if shard else 0)
             ri = slab.row_index(y)
             stored = ri >= 0
             row_ok = 1 <= y <= G.m - 1
@@ -136,9 +140,10 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
                     cxx = cxy = z
             else:
                 cpx = cpy = crx = cry = cxx = cxy = z
-            cpx, cpy = np.where(k0a, cpx, 0.0), np.where(k0b, cpy, 0.0)
-            crx, cry = np.where(k0a, crx, 0.0), np.where(k0b, cry, 0.0)
-            cxx, cxy = np.where(k0a, cxx, 0.0), np.where(k0b, cxy, 0.0)
+            if not full:  # FULL stages read their inputs unmasked (zeros outside the unknowns, stale data only where masked later)
+                cpx, cpy = np.where(k0a, cpx, 0.0), np.where(k0b, cpy, 0.0)
+                crx, cry = np.where(k0a, crx, 0.0), np.where(k0b, cry, 0.0)
+                cxx, cxy = np.where(k0a, cxx, 0.0), np.where(k0b, cxy, 0.0)
             P0x, P0y = crx + beta * cpx, cry + beta * cpy
             LP0, RP0 = shfl_up(P0y), shfl_down(P0x)
             ap0 = stencil(P1x, LP1, P1y, P0x, P2x)
@@ -169,12 +174,7 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
                 gam += float(np.sum(R0x[w] * R0x[w]) + np.sum(R0y[w] * R0y[w]))
             LR0, RR0 = shfl_up(R0y), shfl_down(R0x)
             w = writer & np.ones((warps, 32), dtype=bool)
-            if edge:
-                if ya <= y - 1 < yb:
-                    dh += float(np.sum(R0x[w] * R0y[w]) + np.sum(R0y[w] * RR0[w]))
-                if ya <= y - 2 < yb:
-                    dv += float(np.sum(R1x[w] * R0x[w]) + np.sum(R1y[w] * R0y[w]))
-            elif ya <= y - 2 < yb:
+            if ya <= y - 2 < yb:
                 w0 = stencil(R1x, LR1, R1y, R0x, R2x)
                 w1 = stencil(R1y, R1x, RR1, R0y, R2y)
                 dlt += float(np.sum(R1x[w] * w0[w]) + np.sum(R1y[w] * w1[w]))
@@ -182,15 +182,13 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, ed
             R2x, R2y, R1x, R1y, LR1, RR1 = R1x, R1y, R0x, R0y, LR0, RR0
             r1x, r1y, x1x, x1y, q1x, q1y = crx, cry, cxx, cxy, cpx, cpy
             k1a, k1b = k0a, k0b
-    if edge:
-        dlt = G.A * gam + 2.0 * G.xk * dh + 2.0 * G.yk * dv
     return gam, dlt
 
 
-def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False, warps=8):
+def run(n, m, lshape, iters, tile_rows=0, sms=4, warps=WARPS):
     G = Grid(n, m, lshape)
     domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
-    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2, tile_rows=tile_rows, fused=2 if warps == 7 else 1)
+    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2, tile_rows=tile_rows, fused=True)
     rng = np.random.default_rng(n * 1000 + m)
     b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
 
@@ -218,7 +216,7 @@ def run(n, m, lshape, iters, tile_rows=0, sms=4, edge=False, warps=8):
     for k in range(iters):
         par = k & 1
         g2, d2 = sweep(G, tiles, rb[par], pb[par], x, rb[par ^ 1], pb[par ^ 1], alpha, beta, alpha_prev, x2=bool(k & 1),
-                       edge=edge, warps=warps)
+                       warps=warps)
         worst = max(worst, abs(g2 - hist[k][0]) / hist[k][0], abs(d2 - hist[k][1]) / abs(hist[k][1]))
         alpha_prev = alpha if not (k & 1) else 0.0
         beta = g2 / gamma
@@ -297,20 +295,14 @@ def run_sharded(n, m, lshape, iters, world, sms=4, tile_rows=0):
 
 if __name__ == "__main__":
     for n, m, lshape, iters, tr in [(30, 30, True, 7, 0), (64, 64, True, 6, 0), (64, 64, True, 5, 5), (130, 90, True, 6, 0),
-                                    (77, 33, False, 6, 3), (1000, 40, True, 4, 0), (970, 24, False, 3, 7)]:
-        for edge in (False, True):
-            worst, dx, dr, nt = run(n, m, lshape, iters, tr, edge=edge)
-            print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} {'edge sums' if edge else 'stencil'}: "
-                  f"dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
-            # the edge-sum form of r'.A r' cancels A_diag * gamma' against the edge terms: its dots carry ~1e-11
-            assert worst < (1e-9 if edge else 1e-12) and dx < 1e-10 and dr < 1e-10
+                                    (77, 33, False, 6, 3), (1000, 40, True, 4, 0), (970, 24, False, 3, 7),
+                                    (900, 30, True, 3, 0), (430, 26, False, 3, 4), (845, 64, True, 3, 0)]:
+        worst, dx, dr, nt = run(n, m, lshape, iters, tr)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
+        assert worst < 1e-12 and dx < 1e-10 and dr < 1e-10
     for n, m, lshape, iters, world, tr in [(64, 64, True, 6, 2, 0), (64, 64, True, 5, 3, 0), (130, 90, True, 5, 4, 0),
                                            (77, 60, False, 5, 3, 5), (1000, 40, True, 4, 2, 0), (96, 96, True, 7, 8, 0)]:
         worst, dx, dr = run_sharded(n, m, lshape, iters, world, tile_rows=tr)
         print(f"n={n} m={m} {'L' if lshape else 'rect'} {world} slabs tile_rows={tr}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
-        assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
-    for n, m, lshape, iters, tr in [(64, 64, True, 5, 0), (900, 30, True, 3, 0), (430, 26, False, 3, 4)]:
-        worst, dx, dr, nt = run(n, m, lshape, iters, tr, warps=7)
-        print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} 7 consumer warps: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
         assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
     print("MODEL_OK")

@@ -33,28 +33,26 @@ def main():
     hs2 = {"B200CG_SHAPE_DOT": "0", "B200CG_SHAPE_UPD": "0", "B200CG_SHAPE_NOX": "0"}
     cases = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
              (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb")]
-    if os.environ.get("B200CG_TEST_EXPERIMENTAL") == "1":
-        # "mf-ss": the single-sweep iteration on a sharded plan (two halo rows per side over peer memory) - written
-        # against the CPU model (scripts/model_single_sweep.py: run_sharded) and not yet run on hardware
-        cases += [(256, 0, 1e-8, "mf-ss"), (1100, 0, 1e-6, "mf-ss"), (333, 1, 1e-8, "mf-ss")]
+    # "mf": the default iteration = single sweep on a sharded plan (two halo rows per side over peer memory, one
+    # publish-and-wait per iteration); "mf-2s": the two-sweep iteration
+    cases += [(256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s")]
     for n, domain, eps, kind in cases:
         o = Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
         b, u = o.rhs(), o.true_solution()
         if kind == "mf-hs2":
             os.environ.update(hs2)
-        if kind == "mf-ss":
-            os.environ["B200CG_SINGLE_SWEEP_SHARDED"] = "1"
         plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local, rank=rank, world=world,
                          comm_id=fresh_comm_id())
-        for k in list(hs2) + ["B200CG_SINGLE_SWEEP_SHARDED"]:
+        for k in list(hs2):
             os.environ.pop(k, None)
         lo, hi = plan.lo, plan.hi
         got_cb = []
-        if kind in ("mf", "mf-hs2", "mf-ss"):
+        if kind in ("mf", "mf-hs2", "mf-2s"):
             ref = o.mf_solve(b=b, eps=eps, max_it=20000)
-            x, info = plan.solve(b=b[lo:hi], eps_rel=eps, max_it=20000, single_sweep=1 if kind == "mf-ss" else 2)
-            if kind == "mf-ss" and info["single_sweep"] != 1:
-                failures.append((n, domain, kind, "single sweep not taken"))
+            two = kind != "mf"
+            x, info = plan.solve(b=b[lo:hi], eps_rel=eps, max_it=20000, single_sweep=2 if two else 0)
+            if info["single_sweep"] != (0 if two else 1):
+                failures.append((n, domain, kind, "wrong iteration scheme"))
         elif kind == "cb":
             ref = o.mf_solve(b=b, eps=eps, max_it=20000, with_hist=True)
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], eps_rel=eps, max_it=20000,

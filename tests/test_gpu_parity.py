@@ -211,10 +211,63 @@ def test_interrupt_flag(capi):
                           small_grid_path=1)
         assert info["stop_reason"] == "INTERRUPTED" and not info["converged"]
         assert 0 < info["iterations"] <= 10
+        # inside a long graph launch the loop kernels themselves see the flag: every 16th iteration (both iteration schemes)
+        for ss in (1, 2):
+            x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, iters_per_graph=100, stop_flag=flag,
+                              small_grid_path=1, single_sweep=ss)
+            assert info["stop_reason"] == "INTERRUPTED" and not info["converged"] and info["iterations"] == 16
+        x, info = p.solve(rhs_on_device=True, rule=capi.RULE_MAXNORM, eps_r=1e-30, max_it=100000, iters_per_graph=100,
+                          stop_flag=flag, small_grid_path=1)
+        assert info["stop_reason"] == "INTERRUPTED" and info["iterations"] == 16
+        p.assemble_csr()
+        x, info = p.solve(rhs_on_device=True, op=capi.OP_CSR, rule=capi.RULE_MAXNORM, eps_r=1e-30, max_it=100000,
+                          iters_per_graph=100, stop_flag=flag)
+        assert info["stop_reason"] == "INTERRUPTED" and info["iterations"] == 16
         # cluster-resident kernel: the mapped flag is polled every 128 iterations
         x, info = p.solve(rhs_on_device=True, eps_rel=1e-30, max_it=100000, stop_flag=flag, small_grid_path=2)
         assert info["stop_reason"] == "INTERRUPTED" and not info["converged"] and info["cluster_path"] == 1
         assert 0 < info["iterations"] <= 128
+
+
+def test_dense_callback_cadence_does_not_lap_the_ring(capi):
+    """callback_every = 1 on a long small-grid solve appends more records than the device ring holds (1024): such a solve
+    must stay on the graph path, whose launches are sized to the ring, and deliver every record exactly once."""
+    n = 128
+    with plan_for(capi, n) as p:
+        p.build_rhs()
+        runs = {}
+        for every in (1, 100):
+            got = []
+            x, info = p.solve(rhs_on_device=True, rule=capi.RULE_MAXNORM, eps_p=-1.0, eps_r=1e-30, max_it=1500,
+                              callback_every=every, callback=lambda it, pr, rs, er: got.append((it, pr, rs, er)))
+            runs[every] = (x, info, np.array(got))
+        (x1, i1, g1), (x100, i100, g100) = runs[1], runs[100]
+        assert i1["iterations"] == i100["iterations"] == 1500
+        assert i1["cluster_path"] == 0  # 1503 records do not fit one launch's ring
+        assert np.array_equal(g1[:, 0], np.concatenate([np.arange(0, 1501), [1500]]))  # it 0 .. 2500, then the final call
+        assert np.array_equal(x1, x100) or relmax(x1, x100) < 1e-12
+        sel = np.isin(g1[:-1, 0], g100[:-1, 0])
+        assert np.allclose(g1[:-1][sel], g100[:-1], rtol=1e-9, atol=0)
+
+
+def test_csr_reupload_invalidates_cached_graphs(capi, oracle_mod):
+    """b200cg_set_csr / _assemble_csr free and reallocate the matrix: graphs captured with the old pointers must go."""
+    n = 30
+    o = oracle_for(oracle_mod, n)
+    b = o.rhs()
+    with plan_for(capi, n) as p:
+        nnz = p.assemble_csr()
+        kw = dict(b=b, op=capi.OP_CSR, rule=capi.RULE_MAXNORM, eps_p=-1.0, eps_r=1e-9, max_it=5000)
+        x1, i1 = p.solve(**kw)
+        row_map, entries, values = p.get_csr(nnz)
+        junk = [np.zeros(1 << 20) for _ in range(4)]  # churn the allocator a little
+        p.set_csr(row_map, entries, 2.0 * values)     # A -> 2 A: the solution halves
+        del junk
+        x2, i2 = p.solve(**kw)
+        assert relmax(2.0 * x2, x1) < 1e-8
+        p.assemble_csr()
+        x3, i3 = p.solve(**kw)
+        assert np.array_equal(x3, x1) and i3["iterations"] == i1["iterations"]
 
 
 # ---------------------------------------------------------------- MSGSolver rules (max-norm), both operators

@@ -20,7 +20,7 @@ def unknown_mask(n, m, domain):
     return mask
 
 
-FUSED_STRIP_OUT, FUSED_SHIFT = 480, 2  # csrc/fused_kernel.cuh
+FUSED_STRIP_OUT, FUSED_SHIFT = 420, 2  # csrc/fused_kernel.cuh: 7 consumer warps x 60 columns
 
 
 def coverage(n, m, tiles, strip_out=STRIP_OUT, shift=0):
@@ -48,7 +48,7 @@ def check_split(n, m, domain, world, sms, ctas, weights=None, tile_rows=0, fused
             assert np.all(lower | (tiles[:, 1] > m // 2))
             assert np.all(tiles[lower & (tiles[:, 1] <= m // 2), 3] == n // 2 + 1)
             assert np.all(tiles[tiles[:, 1] > m // 2, 3] == 1)
-        cov = coverage(n, m, tiles, {1: FUSED_STRIP_OUT, 2: 420}[int(fused)], FUSED_SHIFT) if fused else coverage(n, m, tiles)
+        cov = coverage(n, m, tiles, FUSED_STRIP_OUT, FUSED_SHIFT) if fused else coverage(n, m, tiles)
         assert cov.sum() == hi - lo
         total += cov
     assert np.array_equal(total, unknown_mask(n, m, domain))
@@ -109,11 +109,10 @@ def test_small_machines_and_errors():
         capi.work_split(129, 129)  # odd n: not a reference grid
 
 
-@pytest.mark.parametrize("n", [6, 30, 478, 480, 482, 962, 2048])
+@pytest.mark.parametrize("n", [6, 30, 418, 420, 422, 842, 2048])
 def test_single_sweep_strip_geometry(n):
-    """The single-sweep kernel cuts strips of 480 written columns (desc.reserved0 = 1)."""
+    """The single-sweep kernel cuts strips of 420 written columns (desc.reserved0 = 1)."""
     check_split(n, n, capi.DOMAIN_LSHAPE, 1, 148, 2, fused=True)
     check_split(n, n + 3, capi.DOMAIN_RECT, 1, 148, 2, fused=True, tile_rows=3)
     check_split(n + 1, n, capi.DOMAIN_LSHAPE_ANY, 1, 4, 2, fused=True)
-    check_split(n, n, capi.DOMAIN_LSHAPE, 1, 148, 2, fused=2)  # the 7-consumer-warp variant: 420 written columns
-    check_split(n, n + 1, capi.DOMAIN_RECT, 2, 16, 2, fused=2) if n >= 8 else None
+    check_split(n, n + 1, capi.DOMAIN_RECT, 2, 16, 2, fused=True) if n >= 8 else None
