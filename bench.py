@@ -36,7 +36,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cg_gdof_iter_per_s"
 UNIT = "GDOF-iter/s"
-BYTES_MODEL = 80.0        # algorithmic bytes per DOF-iteration of the store-Ap formulation
+BYTES_MODEL = 80.0        # algorithmic bytes per DOF-iteration of the store-Ap formulation (a work MODEL: the
+                          # implementation moves 40 - 56 B, so "GB/s at 80 B" can exceed the physical bandwidth)
+BYTES_CSR = 152.0         # SURVEY 8d, assembled path: 12 nnz + 4 (N+1) + 88 N per iteration with nnz -> 5 N
 BYTES_UPD = 48.0          # update-phase kernel touching x: r, p_old, x in; x, r, p out
 BYTES_UPD_NOX = 32.0      # update-phase kernel of an even iteration under x-deferral: r, p_old in; r, p out
 BYTES_DOT = 16.0          # dot-phase kernel: r, p_old in
@@ -57,8 +59,11 @@ def parse_args():
     ap.add_argument("--domain", default="lshape", choices=["lshape", "rect"])
     ap.add_argument("--op", default="mf", choices=["mf", "csr"])
     ap.add_argument("--single-sweep", type=int, default=0, choices=[0, 1, 2],
-                    help="b200cg_params.single_sweep: 1 = one sweep per iteration (Chronopoulos-Gear alpha), 0 = plan default")
-    ap.add_argument("--no-single-sweep-extra", action="store_true")
+                    help="b200cg_params.single_sweep: 0 = plan default (one sweep per iteration, Chronopoulos-Gear alpha), "
+                         "2 = the two-sweep iteration (alpha = r.r / p.Ap)")
+    ap.add_argument("--no-extras", "--no-single-sweep-extra", dest="no_extras", action="store_true",
+                    help="skip the extra legs (two-sweep iteration on the same grid, assembled-CSR CG at 8192^2)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the in-run sharded parity cases")
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--iters-per-graph", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -80,11 +85,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(single_sweep):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    ncu --set full capture of the 16384^2 workload, if any."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
-        return json.load(open(path)).get("upd_kernel_dram_bytes_per_launch")
+        return json.load(open(path)).get("fused_x2_dram_bytes_per_launch" if single_sweep else "upd_kernel_dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -198,6 +204,46 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
+def csr_roofline(spmv_ms, upd_ms, n_local, nnz, peak, peak_src):
+    """Assembled path: per iteration 12 nnz + 4 (N + 1) + 88 N algorithmic bytes = 152 B/DOF-it at nnz -> 5 N.
+    Dominant kernel: the fused direction update + SpMV + dots (values 8 + columns 4 per non-zero, row_map, z gathered
+    once, r, z_old in, z, Az out)."""
+    spmv_bytes = 12.0 * nnz + 4.0 * (n_local + 1) + 40.0 * n_local  # r, z_old in; z, Az out; gather counted once
+    upd_bytes = 48.0 * n_local                                        # x, z, r, Az in; x, r out
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
+    return {"bound": "hbm", "kernel": "csr_spmv_kernel<1> (direction update + SpMV + dots)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms,
+            "update_kernel": {"achieved": upd_bytes / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else None, "avg_launch_ms": upd_ms,
+                              "algorithmic_bytes_per_launch": upd_bytes},
+            "algorithmic_bytes_per_dof_iter": (spmv_bytes + upd_bytes) / n_local, "model_bytes_per_dof_iter": BYTES_CSR,
+            "single_sweep": False, "x_deferral": False}
+
+
+def csr_leg(capi, device, n, iters, steps, peak, peak_src):
+    """BASELINE.json configs[3]: assembled GridSystem CSR SpMV CG on the n x n grid vs the matrix-free iteration."""
+    with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, device=device) as p:
+        p.build_rhs()
+        nnz = p.assemble_csr()
+        out = {"workload": workload_name(n, iters, "lshape", "csr"), "unknowns": p.N, "nnz": nnz}
+        for name, kw in (("csr", dict(op=capi.OP_CSR)), ("matrix_free", dict(op=capi.OP_MATRIX_FREE))):
+            kw.update(rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=iters, rhs_on_device=True, keep_x_on_device=True)
+            for _ in range(2):
+                p.solve(**kw)
+            ms, its, spmv, upd = 0.0, 0, 0.0, 0.0
+            for _ in range(steps):
+                _, info = p.solve(**kw)
+                ms += info["device_ms"]
+                its += info["iterations"]
+                spmv += info["dot_kernel_ms"]
+                upd += info["upd_kernel_ms"]
+            out[name] = {"value": float(p.N) * its / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms / steps}
+            if name == "csr":
+                out["csr"]["roofline"] = csr_roofline(spmv / steps, upd / steps, p.N, nnz, peak, peak_src)
+        out["csr_vs_matrix_free"] = out["csr"]["value"] / out["matrix_free"]["value"]
+        return out
+
+
 def run_b200(args):
     import torch  # plumbing only: process group, barrier, max-over-ranks
 
@@ -241,14 +287,29 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- N > 1: correctness of the sharded solve on THIS build, on the driver's record (tests/run_multigpu.py cases:
+    # both iteration schemes, both rule sets, callbacks, 2-row stages) - before and outside the timed region
+    parity = None
+    if world > 1 and not args.no_parity:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("run_multigpu", os.path.join(ROOT, "tests", "run_multigpu.py"))
+        mg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mg)
+        t_par = time.perf_counter()
+        try:
+            parity = mg.run_cases(rank, world, local_rank, mg.BENCH_CASES, log=lambda m: print(m, file=sys.stderr, flush=True))
+        except Exception as exc:  # a failing check must not cost the timing line; it is reported as not ok
+            parity = {"cases": len(mg.BENCH_CASES), "ok": False, "error": repr(exc)}
+        parity["seconds"] = time.perf_counter() - t_par
+
     n = grid_side(args.n, world if args.scaling == "weak" else 1, args.domain)
     domain = capi.DOMAIN_LSHAPE if args.domain == "lshape" else capi.DOMAIN_RECT
     op = capi.OP_MATRIX_FREE if args.op == "mf" else capi.OP_CSR
     plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local_rank, rank=rank, world=world,
                      comm_id=comm_id, tile_rows=args.tile_rows)
     plan.build_rhs()  # synthetic, deterministic: the reference's analytic f and Dirichlet data
-    if op == capi.OP_CSR:
-        plan.assemble_csr()
+    plan_nnz = plan.assemble_csr() if op == capi.OP_CSR else 0
     n_local = plan.n_local
     solve_kw = dict(op=op, rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=args.iters, iters_per_graph=args.iters_per_graph,
                     single_sweep=args.single_sweep)
@@ -319,6 +380,8 @@ def run_b200(args):
 
     peak, peak_src = measured_peak()
     roofline = None
+    if samples and op == capi.OP_CSR:
+        roofline = csr_roofline(dot_ms / samples, upd_ms / samples, n_local, plan_nnz, peak, peak_src)
     if samples and op == capi.OP_MATRIX_FREE:
         # dominant kernel = the update phase that touches x (48 B/unknown). Under x-deferral even iterations run
         # the lighter variant (32 B/unknown); both and the dot phase (16 B) are listed.
@@ -331,7 +394,7 @@ def run_b200(args):
         roofline = {"bound": "hbm",
                     "kernel": ("cg_fused_kernel<F_X2> (single-sweep iteration touching x)" if single_sweep
                                else "cg_stream_kernel<MODE_UPD> (update phase touching x)"), "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None if single_sweep else ncu_traffic(),
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(single_sweep) if n == 16384 and world == 1 else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_UPD * n_local,
                     "avg_launch_ms": upd_s * 1e3, "launches_sampled": samples,
                     "x_deferral": bool(xdefer),
@@ -358,50 +421,62 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, args.iters, args.domain, args.op), "grid_n": n, "unknowns": plan.N,
                    "unknowns_per_gpu": plan.N / world, "iterations_per_step": args.iters,
-                   "iteration": "single sweep (b200cg_params.single_sweep = 1)" if single_sweep else "two sweeps (default)",
+                   "iteration": ("single sweep per iteration (default; alpha from the single-reduction CG recurrence)"
+                                 if single_sweep else "two sweeps per iteration (alpha = r.r / p.Ap)"),
                    "parallelism": (f"row-slab x{world}, " + ("NVLink peer-memory halo + reductions" if peer_exchange
                                                             else "NCCL halo + all-reduce")) if world > 1 else "single GPU",
                    "l2": "inputs_exceed_l2" if n_local * 8 > 200e6 else "inputs_fit_l2_no_flush",
                    "timing": "CUDA events on the library's solve stream, summed over steps, max over ranks",
                    "wall_ms_per_step": wall_ms / max(args.steps, 1)},
-        "hbm_gbs_at_80B_per_dof_iter": value * BYTES_MODEL / world,
-        "frac_of_8tbs_per_gpu": value * BYTES_MODEL / world / NOMINAL_HBM_GBS,
+        # real traffic: what the implementation moves (algorithmic bytes of its kernels x value), per GPU
+        "hbm_gbs_actual": (value * roofline["algorithmic_bytes_per_dof_iter"] / world) if roofline else None,
+        "frac_of_measured_peak_actual": (value * roofline["algorithmic_bytes_per_dof_iter"] / world / peak) if roofline else None,
+        "frac_of_8tbs_actual": (value * roofline["algorithmic_bytes_per_dof_iter"] / world / NOMINAL_HBM_GBS) if roofline else None,
+        # equivalent work in SURVEY 8d's 80-byte store-Ap MODEL (not traffic: it may exceed the physical bandwidth)
+        "model_80B": {"model": "80 B/DOF-it (SURVEY 8d: store-Ap formulation)",
+                      "equivalent_gbs_per_gpu": value * BYTES_MODEL / world,
+                      "equivalent_frac_of_8tbs": value * BYTES_MODEL / world / NOMINAL_HBM_GBS},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "single_sweep_extra": None,
+        "multi_gpu_parity": parity, "two_sweep_extra": None, "csr_extra": None,
     }
 
-    # ---- extra (1 GPU, matrix-free): the same workload with the opt-in single-sweep iteration, reported beside the
-    # headline value (which stays on the default path so that every N measures the same code). It runs last, under a
-    # watchdog: whatever happens in it, the line above is printed.
-    if world == 1 and op == capi.OP_MATRIX_FREE and args.single_sweep == 0 and not args.no_single_sweep_extra:
+    # ---- extras (1 GPU, default workload): (1) the same grid with the two-sweep iteration (alpha = r.r / p.Ap, what
+    # the max-norm rules and the report callback run); (2) BASELINE.json configs[3]: assembled-CSR CG at 8192^2 beside
+    # the matrix-free iteration on that grid. They run last, under a watchdog: whatever happens, the line is printed.
+    if world == 1 and op == capi.OP_MATRIX_FREE and args.single_sweep == 0 and not args.no_extras:
         import threading
 
         finished = threading.Event()
 
         def watchdog():
-            if not finished.wait(120.0):
-                line["single_sweep_extra"] = {"error": "timed out"}
+            if not finished.wait(240.0):
+                line.setdefault("extras_error", "timed out")
                 print(json.dumps(line), flush=True)
                 os._exit(0)
 
         threading.Thread(target=watchdog, daemon=True).start()
         try:
-            kw = dict(solve_kw, single_sweep=1)
+            kw = dict(solve_kw, single_sweep=2)
             for _ in range(2):
                 plan.solve(rhs_on_device=True, keep_x_on_device=True, **kw)
-            s_ms, s_its, s_on = 0.0, 0, 0
+            s_ms, s_its, s_on = 0.0, 0, 1
             for _ in range(args.steps):
                 _, info = plan.solve(rhs_on_device=True, keep_x_on_device=True, **kw)
                 s_ms += info["device_ms"]
                 s_its += info["iterations"]
                 s_on = info["single_sweep"]
-            line["single_sweep_extra"] = {
+            line["two_sweep_extra"] = {
                 "value": float(plan.N) * s_its / (s_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": s_ms / max(args.steps, 1),
-                "active": bool(s_on), "algorithmic_bytes_per_dof_iter": 40.0,
-                "note": "b200cg_params.single_sweep = 1: one kernel per iteration, alpha from the single-reduction CG "
-                        "recurrence; same parity bar (tests/test_single_sweep_gpu.py)"}
-        except Exception as exc:  # the extra leg must never cost the headline line
-            line["single_sweep_extra"] = {"error": repr(exc)}
+                "active": not s_on, "algorithmic_bytes_per_dof_iter": 56.0,
+                "dot_kernel_ms": info["dot_kernel_ms"], "upd_even_ms": info["upd_even_ms"], "upd_odd_ms": info["upd_odd_ms"],
+                "note": "b200cg_params.single_sweep = 2: dot sweep + update sweep per iteration, alpha = r.r / p.Ap"}
+        except Exception as exc:  # the extra legs must never cost the headline line
+            line["two_sweep_extra"] = {"error": repr(exc)}
+        try:
+            plan.close()
+            line["csr_extra"] = csr_leg(capi, local_rank, 8192, args.iters, max(2, min(args.steps, 3)), peak, peak_src)
+        except Exception as exc:
+            line["csr_extra"] = {"error": repr(exc)}
         finished.set()
     print(json.dumps(line), flush=True)
     plan.close()

@@ -448,8 +448,6 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_dot = env_int("B200CG_SHAPE_DOT", P->shape_dot);
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
-    P->shape_fused_nox = env_int("B200CG_FUSED_NOX", P->shape_fused_nox);
-    P->shape_fused_x2 = env_int("B200CG_FUSED_X2", P->shape_fused_x2);
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->balance_rounds_fused = P->balance_rounds;

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
     const size_t pitch = (size_t)g.pitch;
     const bool is_out = (tid >= STRIP_HALO / 2) && (tid < CONS_THREADS - STRIP_HALO / 2);
     const int c2 = 2 * tid;  // column inside the strip
-    // the one staged column a warp-edge lane needs from outside its warp (other lanes: any valid column)
+    // the one staged column a warp-edge lane needs from outside its warp
     const int c_edge = (lane == 0) ? max(c2 - 1, 0) : ((lane == 31) ? min(c2 + 2, STRIP_LOAD - 1) : c2);
 
     int stage = 0;
@@ -237,10 +237,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
           pn.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
         }
         // horizontal neighbours: shuffle inside the warp; a warp-edge lane recomputes the one it lacks from the
-        // staged rows (branch-free: every lane loads some column; the strip's two outermost threads, which have no
-        // such neighbour, are halo threads whose results are masked below)
-        double pe = prow[c_edge];
-        if (MODE != MODE_APPLY) pe = __dadd_rn(rrow[c_edge], __dmul_rn(beta, pe));
+        // staged rows (the strip's two outermost threads, which have no such neighbour, are halo threads whose
+        // results are masked below)
+        double pe = 0.0;
+        if (lane == 0 || lane == 31) {  // (all 32 lanes loading 8-byte words at a 16-byte stride = a 2-way bank conflict)
+          pe = prow[c_edge];
+          if (MODE != MODE_APPLY) pe = __dadd_rn(rrow[c_edge], __dmul_rn(beta, pe));
+        }
         double L = __shfl_up_sync(0xffffffffu, pn.y, 1);
         double R = __shfl_down_sync(0xffffffffu, pn.x, 1);
         L = (lane == 0) ? pe : L;

@@ -97,23 +97,13 @@ static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   CU(cudaGetLastError());
   return B200CG_OK;
 }
-// Stage shapes (rows per stage x stages): even iterations stream r, p_old (27 KB per 4-row stage), odd ones also x
-// (41 KB). B200CG_FUSED_NOX / _X2 select the alternatives (tuning knobs, measured in profiles/r2_single_sweep.md).
+// Stage shapes (rows per stage x stages): even iterations stream r, p_old in 4-row stages x 3 (81 KB per CTA), odd ones
+// also x in 4-row stages x 2 (81 KB). Measured against deeper and finer rings (4 x 4, 2 x 8 | 2 x 5, 3 x 3): within
+// 1.5 %, these two on top (profiles/r2_single_sweep.md) - the ring is deep enough, so the alternatives are gone.
 template <int FLAGS>
 static int launch_fused_flags(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if constexpr ((FLAGS & F_X2) != 0) {
-    switch (P->shape_fused_x2) {
-      case 1: return launch_fused_cfg<FLAGS, 2, 5>(P, a, s);
-      case 2: return launch_fused_cfg<FLAGS, 3, 3>(P, a, s);
-      default: return launch_fused_cfg<FLAGS, 4, 2>(P, a, s);
-    }
-  } else {
-    switch (P->shape_fused_nox) {
-      case 1: return launch_fused_cfg<FLAGS, 4, 3>(P, a, s);
-      case 2: return launch_fused_cfg<FLAGS, 2, 8>(P, a, s);
-      default: return launch_fused_cfg<FLAGS, 4, 4>(P, a, s);
-    }
-  }
+  if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2>(P, a, s);
+  else return launch_fused_cfg<FLAGS, 4, 3>(P, a, s);
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {

@@ -15,11 +15,22 @@ from iterative_solvers_b200 import capi  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+FULL_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
+              (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
+              (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s")]
+# bench.py runs these in-process before its timed loop at N > 1 (the oracle solves take ~20 s of rank 0's host time)
+BENCH_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (500, 0, 1e-5, "mf"), (333, 1, 1e-8, "mf"),
+               (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
+               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s")]
+
+
+def run_cases(rank, world, local, cases, log=print):
+    """Every rank calls this inside an initialised NCCL process group. Kinds: "mf" = the default iteration (single sweep:
+    two halo rows per side over peer memory, one publish-and-wait per iteration), "mf-2s" = the two-sweep iteration,
+    "mf-hs2" = two sweeps with 2-row stages (the launch shapes are read when the plan is created), "msg" / "msg0" = the
+    max-norm rules with / without a true solution, "cb" = the per-iteration report callback.
+    Returns {"cases", "ok", "max_rel", "iterations_equal", "failed"} (meaningful on rank 0)."""
+
     def fresh_comm_id():  # an NCCL unique id bootstraps exactly one communicator: one per plan
         blob = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -27,15 +38,8 @@ def main():
         dist.broadcast(blob, src=0)
         return bytes(blob.cpu().tolist())
 
-    failures = []
-    # "mf-hs2": every sweep flavour with 2-row stages (the launch shapes are read when the plan is created);
-    # "msg0": the max-norm rules without a true solution
+    failures, max_rel, its_equal, refs = [], 0.0, True, {}
     hs2 = {"B200CG_SHAPE_DOT": "0", "B200CG_SHAPE_UPD": "0", "B200CG_SHAPE_NOX": "0"}
-    cases = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
-             (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb")]
-    # "mf": the default iteration = single sweep on a sharded plan (two halo rows per side over peer memory, one
-    # publish-and-wait per iteration); "mf-2s": the two-sweep iteration
-    cases += [(256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s")]
     for n, domain, eps, kind in cases:
         o = Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
         b, u = o.rhs(), o.true_solution()
@@ -47,22 +51,32 @@ def main():
             os.environ.pop(k, None)
         lo, hi = plan.lo, plan.hi
         got_cb = []
+
+        def reference(key, fn):  # the oracle is serial host code: only rank 0 needs it, once per distinct solve
+            if rank != 0:
+                return None
+            if key not in refs:
+                refs[key] = fn()
+            return refs[key]
+
+        # the GPU solve first, on all ranks together; rank 0 computes the reference afterwards while the others wait in
+        # the gather below (inside a solve a rank waits at most 20 s for its peers)
         if kind in ("mf", "mf-hs2", "mf-2s"):
-            ref = o.mf_solve(b=b, eps=eps, max_it=20000)
             two = kind != "mf"
             x, info = plan.solve(b=b[lo:hi], eps_rel=eps, max_it=20000, single_sweep=2 if two else 0)
             if info["single_sweep"] != (0 if two else 1):
                 failures.append((n, domain, kind, "wrong iteration scheme"))
+            ref = reference((n, domain, eps, "mf"), lambda: o.mf_solve(b=b, eps=eps, max_it=20000))
         elif kind == "cb":
-            ref = o.mf_solve(b=b, eps=eps, max_it=20000, with_hist=True)
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], eps_rel=eps, max_it=20000,
                                  callback=lambda it, p, r, e: got_cb.append((it, p, r, e)))
+            ref = reference((n, domain, eps, "cb"), lambda: o.mf_solve(b=b, eps=eps, max_it=20000, with_hist=True))
         elif kind == "msg0":
-            ref = o.msg_solve(b=b, eps_p=eps, eps_r=eps, max_it=20000)
             x, info = plan.solve(b=b[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
+            ref = reference((n, domain, eps, "msg0"), lambda: o.msg_solve(b=b, eps_p=eps, eps_r=eps, max_it=20000))
         else:
-            ref = o.msg_solve(b=b, u=u, eps_p=eps, eps_r=eps, max_it=20000)
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
+            ref = reference((n, domain, eps, "msg"), lambda: o.msg_solve(b=b, u=u, eps_p=eps, eps_r=eps, max_it=20000))
         v = np.random.default_rng(n).standard_normal(o.N)
         y = plan.apply(v[lo:hi])
         res, _ = plan.postprocess(want_error=False)
@@ -73,7 +87,9 @@ def main():
             xg, yg, rg = np.empty(o.N), np.empty(o.N), np.empty(o.N)
             for plo, phi, px, py, pr in parts:
                 xg[plo:phi], yg[plo:phi], rg[plo:phi] = px, py, pr
-            rel = np.max(np.abs(xg - ref["x"])) / np.max(np.abs(ref["x"]))
+            rel = float(np.max(np.abs(xg - ref["x"])) / np.max(np.abs(ref["x"])))
+            max_rel = max(max_rel, rel)
+            its_equal = its_equal and info["iterations"] == ref["iterations"]
             ok = abs(info["iterations"] - ref["iterations"]) <= 1 and rel < 1e-10
             ok = ok and np.array_equal(yg, o.apply(v))
             ok = ok and np.max(np.abs(rg - (o.apply(xg) - b))) <= 1e-12 * np.max(np.abs(b))
@@ -83,16 +99,27 @@ def main():
                 got = np.array(got_cb)
                 ok = ok and len(got) == len(ref["hist"]) and np.all(
                     np.abs(got[:, 1:] - ref["hist"]) <= 1e-9 * np.max(np.abs(ref["hist"]), axis=0) + 1e-9 * np.abs(ref["hist"]))
-            print(f"[multigpu] n={n} domain={domain} {kind} (peer_exchange={info['peer_exchange']}): "
-                  f"iterations {info['iterations']} vs {ref['iterations']}, "
-                  f"max rel diff {rel:.2e} -> {'ok' if ok else 'FAIL'}", flush=True)
+            log(f"[multigpu] n={n} domain={domain} {kind} (peer_exchange={info['peer_exchange']}, "
+                f"single_sweep={info['single_sweep']}): iterations {info['iterations']} vs {ref['iterations']}, "
+                f"max rel diff {rel:.2e} -> {'ok' if ok else 'FAIL'}")
             if not ok:
                 failures.append((n, domain, kind))
     dist.barrier()
+    return {"cases": len(cases), "ok": not failures, "max_rel": max_rel, "iterations_equal": bool(its_equal),
+            "failed": [list(map(str, f)) for f in failures], "world": world,
+            "bar": "iterations within +-1 of the CPU oracle, solution within 1e-10 relative, apply bit-equal"}
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run_cases(rank, world, local, FULL_CASES, log=lambda m: print(m, flush=True))
     dist.destroy_process_group()
     if rank == 0:
-        print("MULTIGPU_OK" if not failures else f"MULTIGPU_FAIL {failures}", flush=True)
-        sys.exit(1 if failures else 0)
+        print("MULTIGPU_OK" if out["ok"] else f"MULTIGPU_FAIL {out['failed']}", flush=True)
+        sys.exit(0 if out["ok"] else 1)
 
 
 if __name__ == "__main__":

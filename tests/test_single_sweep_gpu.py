@@ -119,27 +119,3 @@ def test_large_grid_property(capi):
         assert isf["iterations"] == idf["iterations"] == 60
         assert relmax(xs, xd) < 1e-11
         assert abs(isf["r_l2"] - idf["r_l2"]) <= 1e-10 * idf["r_l2"]
-
-
-@pytest.mark.parametrize("env", [{"B200CG_FUSED_NOX": "1"}, {"B200CG_FUSED_NOX": "2", "B200CG_FUSED_X2": "1"},
-                                 {"B200CG_FUSED_X2": "2"}])
-def test_stage_shapes_do_not_change_the_answer(capi, oracle_mod, env):
-    """The stage shapes of the two flavours (rows per stage x stages) are execution strategy only."""
-    import os
-
-    saved = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        for n, domain, tile_rows, eps in [(64, 0, 0, 1e-8), (64, 0, 3, 1e-8), (600, 0, 0, 1e-6), (333, 1, 5, 1e-8)]:
-            o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
-            ref = o.mf_solve(eps=eps, max_it=20000)
-            with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, tile_rows=tile_rows) as p:  # knobs read here
-                x, info = fused_solve(p, b=o.rhs(), eps_rel=eps, max_it=20000)
-                assert abs(info["iterations"] - ref["iterations"]) <= 1
-                assert relmax(x, ref["x"]) < REL
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
