@@ -107,14 +107,19 @@ static inline int csr_ensure_vectors(CsrData* c, cudaStream_t s, std::string* er
   return 0;
 }
 
+// A matrix of the shape already resident is copied into the existing buffers (*reallocated = false: graphs captured
+// with these pointers stay valid); any other shape frees and reallocates everything.
 static inline int csr_upload(CsrData* c, long long nrows, long long nnz, const int* row_map, const int* entries,
-                             const double* values, cudaStream_t s, std::string* err) {
-  csr_free(c);
-  c->nrows = nrows;
-  c->nnz = nnz;
-  CSR_CU(cudaMalloc(&c->row_map, (size_t)(nrows + 1) * sizeof(int)));
-  CSR_CU(cudaMalloc(&c->entries, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
-  CSR_CU(cudaMalloc(&c->values, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
+                             const double* values, cudaStream_t s, std::string* err, bool* reallocated) {
+  *reallocated = !(c->row_map && c->nrows == nrows && c->nnz == nnz);
+  if (*reallocated) {
+    csr_free(c);
+    c->nrows = nrows;
+    c->nnz = nnz;
+    CSR_CU(cudaMalloc(&c->row_map, (size_t)(nrows + 1) * sizeof(int)));
+    CSR_CU(cudaMalloc(&c->entries, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
+    CSR_CU(cudaMalloc(&c->values, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
+  }
   CSR_CU(cudaMemcpyAsync(c->row_map, row_map, (size_t)(nrows + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
   CSR_CU(cudaMemcpyAsync(c->entries, entries, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, s));
   CSR_CU(cudaMemcpyAsync(c->values, values, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, s));

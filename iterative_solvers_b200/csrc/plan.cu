@@ -686,10 +686,13 @@ extern "C" int b200cg_set_csr(b200cg_plan_t P, int64_t nrows, int64_t nnz, const
   if (P->desc.world > 1) return fail(B200CG_ERR_UNSUPPORTED, "the CSR comparison path is single-GPU");
   if (nrows != P->n_global) return fail(B200CG_ERR_INVALID_ARG, "nrows %lld != unknowns %lld", (long long)nrows, (long long)P->n_global);
   CU(cudaSetDevice(P->desc.device));
-  drop_graphs(P, V_CSR);  // they captured the buffers csr_upload frees
-  if (P->solution_in_csr) P->have_solution = P->solution_in_csr = false;  // the solution lived in the freed vectors
   std::string err;
-  int rc = csr_upload(&P->csr, nrows, nnz, row_map, entries, values, P->stream, &err);
+  bool reallocated = false;
+  int rc = csr_upload(&P->csr, nrows, nnz, row_map, entries, values, P->stream, &err, &reallocated);
+  if (reallocated) {
+    drop_graphs(P, V_CSR);  // they captured the buffers csr_upload freed
+    if (P->solution_in_csr) P->have_solution = P->solution_in_csr = false;  // the solution lived in the freed vectors
+  }
   if (rc) return fail(rc, "%s", err.c_str());
   return B200CG_OK;
 }

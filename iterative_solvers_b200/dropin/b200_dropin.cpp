@@ -83,7 +83,16 @@ using b200::check;
 void KokkosSparse::spmv(const char mode[], double alpha, const KokkosCrsMatrix& A, const KokkosVector& x, double beta,
                         const KokkosVector& y) {
   if (!mode || mode[0] != 'N') throw std::invalid_argument("KokkosSparse::spmv: only mode \"N\" is supported");
-  b200::PlanPtr plan = b200::make_generic_plan(A.numRows());
+  // One plan per calling thread and matrix size is kept between calls (stream, events, device buffers; b200cg_set_csr
+  // reuses buffers of the right size). The matrix CONTENTS are uploaded on every call: the Views are plain host
+  // memory the caller may have rewritten since.
+  static thread_local b200::PlanPtr cached;
+  static thread_local long long cached_rows = -1;
+  if (!cached || cached_rows != A.numRows()) {
+    cached = b200::make_generic_plan(A.numRows());
+    cached_rows = A.numRows();
+  }
+  b200::PlanPtr plan = cached;
   b200::upload_matrix(plan, A);
   std::vector<double> ax(static_cast<size_t>(A.numRows()));
   check(b200cg_csr_apply(plan->get(), x.data(), ax.data()));
@@ -115,10 +124,10 @@ KokkosVector MSGSolver::solve(const KokkosVector& true_solution) {
   stop_requested.store(0);
   const long long rows = static_cast<long long>(b.extent(0));
   if (!plan_) plan_ = b200::make_generic_plan(rows);
-  if (!plan_->has_matrix) b200::upload_matrix(plan_, a);
+  if (!matrix_free_ && !plan_->has_matrix) b200::upload_matrix(plan_, a);
 
   b200cg_params prm = {};
-  prm.op = B200CG_OP_CSR;
+  prm.op = matrix_free_ ? B200CG_OP_MATRIX_FREE : B200CG_OP_CSR;
   prm.rule = B200CG_RULE_MAXNORM;
   prm.eps_p = eps_precision;
   prm.eps_r = eps_residual;
@@ -179,17 +188,9 @@ GridSystem::GridSystem(int m_, int n_, double a_, double b_, double c_, double d
     : n(n_), m(m_), a(a_), b(b_), c(c_), d(d_) {
   if (!Kokkos::is_initialized()) Kokkos::initialize();  // grid_system.cpp:304-306
   plan_ = b200::make_geometric_plan(m, n, a, b, c, d);
-  int64_t rows = 0, nnz = 0;
+  int64_t rows = 0;
   check(b200cg_size(plan_->get(), &rows));
-  // assembly on the device (grid_system.cpp:157-274), then mirrored into the host containers the API exposes
-  check(b200cg_assemble_csr(plan_->get(), &nnz));
-  plan_->has_matrix = true;
-  Kokkos::View<int*, memory_space> row_map("row_map", static_cast<size_t>(rows + 1));
-  Kokkos::View<int*, memory_space> entries("entries", static_cast<size_t>(nnz));
-  Kokkos::View<double*, memory_space> values("values", static_cast<size_t>(nnz));
-  check(b200cg_get_csr(plan_->get(), row_map.data(), entries.data(), values.data()));
-  matrix = KokkosCrsMatrix("A", static_cast<int>(rows), static_cast<int>(rows), static_cast<int>(nnz), values, row_map,
-                           entries);
+  rows_ = rows;
   rhs = KokkosVector("rhs", static_cast<size_t>(rows));
   check(b200cg_build_rhs(plan_->get()));
   check(b200cg_get_rhs(plan_->get(), rhs.data()));
@@ -200,17 +201,38 @@ GridSystem::GridSystem(int m_, int n_, double a_, double b_, double c_, double d
 
 GridSystem::~GridSystem() = default;
 
+// assembly on the device (grid_system.cpp:157-274), on first use
+void GridSystem::ensure_device_matrix() const {
+  if (nnz_ >= 0) return;
+  int64_t nnz = 0;
+  check(b200cg_assemble_csr(plan_->get(), &nnz));
+  plan_->has_matrix = true;
+  nnz_ = nnz;
+}
+
+// ... and its mirror in the host containers the API exposes, on first use
+void GridSystem::ensure_matrix() const {
+  if (matrix.numRows() > 0 || rows_ == 0) return;
+  ensure_device_matrix();
+  Kokkos::View<int*, memory_space> row_map("row_map", static_cast<size_t>(rows_ + 1));
+  Kokkos::View<int*, memory_space> entries("entries", static_cast<size_t>(nnz_));
+  Kokkos::View<double*, memory_space> values("values", static_cast<size_t>(nnz_));
+  check(b200cg_get_csr(plan_->get(), row_map.data(), entries.data(), values.data()));
+  matrix = KokkosCrsMatrix("A", static_cast<int>(rows_), static_cast<int>(rows_), static_cast<int>(nnz_), values, row_map,
+                           entries);
+}
+
 KokkosVector GridSystem::get_true_solution_vector() {
-  if (matrix.numRows() == 0)
+  if (rows_ == 0)
     throw std::runtime_error("Matrix not initialized, cannot determine size for true solution vector.");
-  KokkosVector u("true_u", static_cast<size_t>(matrix.numRows()));
+  KokkosVector u("true_u", static_cast<size_t>(rows_));
   check(b200cg_get_true_solution(plan_->get(), u.data()));
   return u;
 }
 
 GridSystem::NodeCoordinates GridSystem::get_node_coordinates(int solution_index) const {
   NodeCoordinates at{0.0, 0.0};  // zero coordinates for an index outside the system (grid_system.cpp:339-341)
-  if (solution_index >= 0 && solution_index < matrix.numRows()) {
+  if (solution_index >= 0 && solution_index < rows_) {
     at.x = node_x_coords[static_cast<size_t>(solution_index)];
     at.y = node_y_coords[static_cast<size_t>(solution_index)];
   }
@@ -218,6 +240,7 @@ GridSystem::NodeCoordinates GridSystem::get_node_coordinates(int solution_index)
 }
 
 std::ostream& operator<<(std::ostream& os, const GridSystem& grid) {
+  grid.ensure_matrix();
   const double rows = grid.matrix.numRows(), cols = grid.matrix.numCols();
   os << "GridSystem Matrix Information:" << std::endl
      << "  Dimensions: " << grid.n << "x" << grid.m << std::endl
@@ -328,9 +351,15 @@ void DirichletSolver::setIterationCallback(std::function<void(int, double, doubl
 
 SolverResults DirichletSolver::solve() {
   if (!grid) throw std::runtime_error("Сетка не инициализирована");
-  solver = std::make_unique<MSGSolver>(grid->get_matrix(), grid->get_rhs(),
+  // The operator: the grid's plan applies the 5-point stencil on the fly - the same matrix GridSystem assembles, bit for
+  // bit, at 40 % of the traffic - unless B200CG_DIRICHLET_OPERATOR=csr asks for the assembled arrays (then the matrix
+  // is assembled on the device; neither way needs its host mirror).
+  const char* op_env = std::getenv("B200CG_DIRICHLET_OPERATOR");
+  const bool matrix_free = !(op_env && std::string(op_env) == "csr");
+  if (!matrix_free) grid->ensure_device_matrix();
+  solver = std::make_unique<MSGSolver>(grid->matrix_handle(), grid->get_rhs(),
                                        std::min({eps_precision, eps_residual, eps_exact_error}), max_iterations);
-  solver->attachPlan(grid->plan());  // the matrix is already resident on the device
+  solver->attachPlan(grid->plan(), matrix_free);
   // a disabled rule is passed as -1 (dirichlet_solver.cpp:71-87)
   solver->setPrecisionEps(use_precision_stopping ? eps_precision : -1.0);
   solver->setResidualEps(use_residual_stopping ? eps_residual : -1.0);
@@ -348,7 +377,8 @@ SolverResults DirichletSolver::solve() {
   results.residual.resize(rows);
   results.error.resize(rows);
   // A x - b and x - u on the device (dirichlet_solver.cpp:147-180)
-  check(b200cg_postprocess(grid->plan()->get(), B200CG_OP_CSR, results.residual.data(), results.error.data()));
+  check(b200cg_postprocess(grid->plan()->get(), matrix_free ? B200CG_OP_MATRIX_FREE : B200CG_OP_CSR, results.residual.data(),
+                           results.error.data()));
   results.x_coords = grid->get_x_coords();
   results.y_coords = grid->get_y_coords();
   results.iterations = solver->getIterations();

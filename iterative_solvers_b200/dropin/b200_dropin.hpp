@@ -103,9 +103,15 @@ class MSGSolver : public Solver {
   KokkosVector solve(const KokkosVector& true_solution) override;
   std::string generateReport(int n, int m, double a, double b, double c, double d) const;
 
-  // B200 additions (not in the reference): reuse an existing geometric plan that already holds this matrix
-  // (DirichletSolver passes its GridSystem's) and expose the device timing of the last solve.
-  void attachPlan(const b200::PlanPtr& plan) { plan_ = plan; }
+  // B200 additions (not in the reference): reuse an existing geometric plan (DirichletSolver passes its GridSystem's)
+  // and expose the device timing of the last solve. matrix_free = true: the plan's geometry IS this matrix
+  // (GridSystem assembled it from that geometry), so the iteration applies the 5-point operator on the fly instead
+  // of reading the CSR arrays - bit-identical operator (tests: csr_apply == apply), ~2.5x less memory traffic.
+  void attachPlan(const b200::PlanPtr& plan, bool matrix_free = false) {
+    plan_ = plan;
+    matrix_free_ = matrix_free;
+  }
+  bool usesMatrixFreeOperator() const { return matrix_free_; }
   const b200::PlanPtr& plan() const { return plan_; }
   double lastSolveMilliseconds() const { return last_solve_ms; }
 
@@ -117,7 +123,7 @@ class MSGSolver : public Solver {
   std::function<void(int, double, double, double)> iteration_callback;
   std::atomic<int> stop_requested;  // polled by b200cg_solve between graph launches
   b200::PlanPtr plan_;
-  bool matrix_uploaded = false;
+  bool matrix_free_ = false;
   double last_solve_ms = 0.0;
 };
 
@@ -132,7 +138,12 @@ class GridSystem {
   GridSystem(int m, int n, double a, double b, double c, double d);
   ~GridSystem();
 
-  const KokkosCrsMatrix& get_matrix() const { return matrix; }
+  // The CSR arrays are assembled on the device and mirrored into the host containers the first time someone asks for
+  // them (3 GB at 8192^2): a DirichletSolver on the matrix-free operator never does.
+  const KokkosCrsMatrix& get_matrix() const {
+    ensure_matrix();
+    return matrix;
+  }
   const KokkosVector& get_rhs() const { return rhs; }
   KokkosVector get_true_solution_vector();
   const std::vector<double>& get_x_coords() const { return node_x_coords; }
@@ -141,12 +152,19 @@ class GridSystem {
 
   friend std::ostream& operator<<(std::ostream& os, const GridSystem& grid);
 
-  const b200::PlanPtr& plan() const { return plan_; }  // B200 addition
+  // B200 additions
+  const b200::PlanPtr& plan() const { return plan_; }
+  const KokkosCrsMatrix& matrix_handle() const { return matrix; }  // the member itself, without forcing the assembly
+  void ensure_device_matrix() const;                               // CSR resident on the device (no host mirror)
+  long long rows() const { return rows_; }
 
  private:
+  void ensure_matrix() const;
   int n, m;
   double a, b, c, d;
-  KokkosCrsMatrix matrix;
+  long long rows_ = 0;
+  mutable long long nnz_ = -1;  // -1: not assembled yet
+  mutable KokkosCrsMatrix matrix;
   KokkosVector rhs;
   std::vector<double> node_x_coords, node_y_coords;
   b200::PlanPtr plan_;
