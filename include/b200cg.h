@@ -60,6 +60,11 @@ typedef enum {
                               beta = (||r'||_2)^2 / r.z (msg_solver.cpp:96-102,165) */
 } b200cg_rule;
 
+typedef enum {
+  B200CG_PRECOND_NONE = 0,      /* the reference's iteration */
+  B200CG_PRECOND_MULTIGRID = 1  /* V(2,2) cycle, damped Jacobi, full weighting / bilinear, rediscretised coarse operators */
+} b200cg_preconditioner;
+
 /* Same values as the reference's enum class StopCriterion (msg_solver.hpp:9-15). */
 typedef enum {
   B200CG_STOP_ITERATIONS = 0,
@@ -110,7 +115,12 @@ typedef struct {
                               sharded plans it needs the peer-memory exchange and >= 4 rows per rank. 0 = the plan's
                               default (on unless B200CG_SINGLE_SWEEP=0), 1 = on, 2 = never (the two-sweep iteration with
                               alpha = r.r / p.Ap). Ignored where it does not apply */
-  int reserved[5];
+  int preconditioner;      /* b200cg_preconditioner. B200CG_PRECOND_MULTIGRID (opt-in; the reference has no preconditioner,
+                              solver.hpp:17-66 is the base class kept for one): CG preconditioned by a geometric-multigrid
+                              V-cycle - matrix-free operator, RULE_REL_L2, no callback, single-GPU plan; the iteration
+                              count no longer grows with n (7 instead of ~2.7 n). Same x0, same stop rule; the iterates
+                              are NOT the reference's (a different Krylov space), only the solution agrees */
+  int reserved[4];
 } b200cg_params;
 
 typedef struct {
@@ -140,7 +150,8 @@ typedef struct {
   int peer_exchange;       /* sharded plans: 1 if halo rows and reductions went over NVLink peer memory (CUDA IPC),
                               0 if over NCCL send/recv + all-reduce */
   int single_sweep;        /* 1 if this solve ran the single-sweep iteration (b200cg_params.single_sweep) */
-  int reserved[2];
+  int preconditioner;      /* b200cg_preconditioner this solve ran with */
+  int mg_levels;           /* multigrid levels used (0 without the preconditioner) */
 } b200cg_info;
 
 /* (iteration, precision, residual, error) - Solver::setIterationCallback, solver.hpp:46-50. Called on the

@@ -33,7 +33,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "b200cg.h")]
     if force or _newer(LIB, deps):
         # one nvcc per translation unit, in parallel (the sweep-kernel instantiations dominate the build time)
-        units = ["plan.cu", "solve.cu", "comm.cu"]
+        units = ["plan.cu", "solve.cu", "comm.cu", "mg.cu"]
         objs = [os.path.join(CSRC, u[:-3] + ".o") for u in units]
         flags = [*ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + (["-Xptxas=-v"] if verbose else [])
         procs = [subprocess.Popen([NVCC, *flags, "-c", os.path.join(CSRC, u), "-o", o]) for u, o in zip(units, objs)]

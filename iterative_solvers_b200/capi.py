@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("B200CG_LIB", os.path.join(PKG, "libb200cg.so"))
 DOMAIN_LSHAPE, DOMAIN_RECT, DOMAIN_GENERIC, DOMAIN_LSHAPE_ANY = 0, 1, 2, 3
 OP_MATRIX_FREE, OP_CSR = 0, 1
 RULE_REL_L2, RULE_MAXNORM = 0, 1
+PRECOND_NONE, PRECOND_MULTIGRID = 0, 1
 STOP_NAMES = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]
 ERR_NO_DEVICE = 2
 
@@ -43,7 +44,8 @@ class Params(C.Structure):
     _fields_ = [("op", C.c_int), ("rule", C.c_int), ("eps_rel", C.c_double), ("eps_p", C.c_double),
                 ("eps_r", C.c_double), ("eps_e", C.c_double), ("max_it", C.c_int), ("callback_every", C.c_int),
                 ("rhs_on_device", C.c_int), ("keep_x_on_device", C.c_int), ("iters_per_graph", C.c_int),
-                ("small_grid_path", C.c_int), ("single_sweep", C.c_int), ("reserved", C.c_int * 5)]
+                ("small_grid_path", C.c_int), ("single_sweep", C.c_int), ("preconditioner", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class SolveInfo(C.Structure):
@@ -55,7 +57,7 @@ class SolveInfo(C.Structure):
                 ("upd_kernel_ms", C.c_double), ("kernel_samples", C.c_int), ("local_unknowns", C.c_int64),
                 ("upd_even_ms", C.c_double), ("upd_odd_ms", C.c_double), ("x_deferral", C.c_int),
                 ("cluster_path", C.c_int), ("peer_exchange", C.c_int), ("single_sweep", C.c_int),
-                ("reserved", C.c_int * 2)]
+                ("preconditioner", C.c_int), ("mg_levels", C.c_int)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -276,12 +278,14 @@ class Plan:
     # ---- solve
     def solve(self, b=None, u=None, x_out=None, op=OP_MATRIX_FREE, rule=RULE_REL_L2, eps_rel=1e-6, eps_p=-1.0,
               eps_r=-1.0, eps_e=-1.0, max_it=10000, callback=None, callback_every=100, rhs_on_device=False,
-              keep_x_on_device=False, iters_per_graph=0, stop_flag=None, small_grid_path=0, single_sweep=0):
+              keep_x_on_device=False, iters_per_graph=0, stop_flag=None, small_grid_path=0, single_sweep=0,
+              preconditioner=0):
         """Returns (x, info dict). b / u / x_out may be numpy arrays or PinnedArray.array views."""
         prm = Params(op=op, rule=rule, eps_rel=eps_rel, eps_p=eps_p, eps_r=eps_r, eps_e=eps_e, max_it=int(max_it),
                      callback_every=int(callback_every), rhs_on_device=int(bool(rhs_on_device)),
                      keep_x_on_device=int(bool(keep_x_on_device)), iters_per_graph=int(iters_per_graph),
-                     small_grid_path=int(small_grid_path), single_sweep=int(single_sweep))
+                     small_grid_path=int(small_grid_path), single_sweep=int(single_sweep),
+                     preconditioner=int(preconditioner))
         if b is not None:
             b = np.ascontiguousarray(b, dtype=np.float64)
             assert b.shape == (self.n_local,)

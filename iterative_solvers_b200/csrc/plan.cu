@@ -2,6 +2,7 @@
 // the CSR entry points of the C ABI (include/b200cg.h). The solve loop lives in solve.cu.
 // No CPU fallback: every compute entry point fails loudly without a CUDA device.
 #include "plan.h"
+#include "mg.h"
 
 using namespace b200cg;
 
@@ -365,6 +366,7 @@ static void free_plan(b200cg_plan_s* P) {
   cudaFree(P->d_links);
   comm_destroy(&P->comm);
   csr_free(&P->csr);
+  mg_free(P);
   for (int i = 0; i < 2; ++i) {
     cudaFree(P->r[i]);
     cudaFree(P->p[i]);

@@ -48,6 +48,8 @@ int b200cg_fail(int code, const char* fmt, ...);
 
 namespace b200cg {
 
+struct MgHierarchy;  // mg.cu
+
 double now_ms();
 
 // ------------------------------------------------------------------------------------------- plan
@@ -127,6 +129,7 @@ struct b200cg_plan_s {
   unsigned long long peer_epoch[2] = {0, 0};
   int64_t n_global = 0;
   std::vector<int> ycuts;  // row cuts of all ranks
+  MgHierarchy* mg = nullptr;  // level hierarchy of the opt-in multigrid preconditioner (built by the first solve that asks)
 };
 
 namespace b200cg {

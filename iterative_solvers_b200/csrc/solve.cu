@@ -1,6 +1,7 @@
 // libb200cg, host side 2/2: the operator and solve entry points - CUDA-graph captured CG loop with device-resident
 // scalars, the single-cluster small-grid path, feedback balancing between launches, post-processing.
 #include "sweep_launch.cuh"
+#include "mg.h"
 
 using namespace b200cg;
 
@@ -231,6 +232,11 @@ static int check_solve_args(b200cg_plan_t P, const b200cg_params* prm, const dou
   if (!prm->keep_x_on_device && !x_host) return fail(B200CG_ERR_INVALID_ARG, "x_host is NULL and keep_x_on_device is 0");
   const bool csr = prm->op == B200CG_OP_CSR;
   if (!csr) NEED_GEOMETRY(P);
+  if (prm->preconditioner != B200CG_PRECOND_NONE && prm->preconditioner != B200CG_PRECOND_MULTIGRID)
+    return fail(B200CG_ERR_INVALID_ARG, "unknown preconditioner %d", prm->preconditioner);
+  if (prm->preconditioner == B200CG_PRECOND_MULTIGRID && (csr || prm->rule != B200CG_RULE_REL_L2 || cb || P->desc.world > 1))
+    return fail(B200CG_ERR_UNSUPPORTED, "the multigrid preconditioner serves the matrix-free operator under the relative-residual "
+                                        "rule without a report callback on a single-GPU plan");
   if (csr && !P->csr.row_map) return fail(B200CG_ERR_STATE, "CSR solve without a matrix: call b200cg_set_csr / b200cg_assemble_csr");
   if (csr && prm->rule == B200CG_RULE_REL_L2 && cb) return fail(B200CG_ERR_UNSUPPORTED, "per-iteration report callbacks exist only on the matrix-free path");
   return B200CG_OK;
@@ -586,9 +592,20 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
       return fail(B200CG_ERR_UNSUPPORTED, "small_grid_path = 2 but this solve cannot run in one cluster "
                                           "(grid too large, sharded plan, CSR operator or per-iteration report)");
   }
-  c.use_cluster = cl_ctas > 0;
-  if (c.use_cluster) RET(run_cluster_solve(c, cl_ctas, cl_rows, cl_smem));
-  else RET(run_graph_solve(c));
+  const bool mg = prm->preconditioner == B200CG_PRECOND_MULTIGRID;
+  c.use_cluster = cl_ctas > 0 && !mg;
+  if (mg) {
+    // opt-in: CG preconditioned by a multigrid V-cycle (mg.cu) - its own loop, same init kernel and stop rule
+    RET(launch_init(c));
+    CU(cudaEventRecord(P->ev[5], s));
+    RET(mg_pcg_solve(P, stop_flag, &info->kernel_launches, &c.interrupted));
+    info->preconditioner = B200CG_PRECOND_MULTIGRID;
+    info->mg_levels = mg_levels(P);
+  } else if (c.use_cluster) {
+    RET(run_cluster_solve(c, cl_ctas, cl_rows, cl_smem));
+  } else {
+    RET(run_graph_solve(c));
+  }
   CU(cudaEventRecord(P->ev[6], s));
 
   const DevState st = *P->h_state;

@@ -251,6 +251,34 @@ std::ostream& operator<<(std::ostream& os, const GridSystem& grid) {
   return os;
 }
 
+// ------------------------------------------------------------------------------------------------- preconditioned CG
+MultigridPCGSolver::MultigridPCGSolver(const GridSystem& grid, double eps_, int maxIterations_)
+    : Solver(grid.matrix_handle(), grid.get_rhs(), eps_, maxIterations_, "МСГ с многосеточным предобуславливателем"),
+      plan_(grid.plan()) {}
+
+MultigridPCGSolver::~MultigridPCGSolver() = default;
+
+KokkosVector MultigridPCGSolver::solve(const KokkosVector& /*true_solution*/) {
+  b200cg_params prm = {};
+  prm.op = B200CG_OP_MATRIX_FREE;
+  prm.rule = B200CG_RULE_REL_L2;
+  prm.eps_rel = eps;
+  prm.max_it = maxIterations;
+  prm.preconditioner = B200CG_PRECOND_MULTIGRID;
+  b200cg_info info = {};
+  KokkosVector x("x", b.extent(0));
+  check(b200cg_solve(plan_->get(), &prm, b.data(), nullptr, x.data(), &info, nullptr, nullptr, nullptr));
+  iterations = info.iterations;
+  converged = info.converged != 0;
+  r0_l2 = info.r0_l2;
+  r_l2 = info.r_l2;
+  levels = info.mg_levels;
+  last_solve_ms = info.solve_ms;
+  if (completion_callback)
+    completion_callback(converged, converged ? "Converged successfully" : "Failed to converge within maximum iterations");
+  return x;
+}
+
 // ------------------------------------------------------------------------------------------------- matrix-free
 MatrixFreeSystem::MatrixFreeSystem(int m_, int n_, double a_, double b_, double c_, double d_)
     : n(n_), m(m_), a(a_), b(b_), c(c_), d(d_) {
@@ -295,6 +323,7 @@ std::vector<double> MatrixFreeSolver::solve(const std::vector<double>& true_solu
   prm.rule = B200CG_RULE_REL_L2;
   prm.eps_rel = eps;
   prm.max_it = maxIterations;
+  prm.preconditioner = multigrid ? B200CG_PRECOND_MULTIGRID : B200CG_PRECOND_NONE;
   b200cg_info info = {};
   std::vector<double> x(rows);
   b200::CallbackBox box{&iteration_callback};

@@ -114,6 +114,33 @@ int cmd_mf(char** a) {
   return 0;
 }
 
+// the opt-in multigrid-preconditioned CG through both doors: the Solver subclass on a GridSystem and the switch of
+// MatrixFreeSolver
+int cmd_mgpcg(char** a) {
+  const int n = std::atoi(a[0]);
+  const double lo = std::atof(a[1]), hi = std::atof(a[2]), eps = std::atof(a[3]);
+  const int max_it = std::atoi(a[4]);
+  GridSystem grid(n, n, lo, hi, lo, hi);
+  MultigridPCGSolver solver(grid, eps, max_it);
+  int completions = 0;
+  solver.setCompletionCallback([&](bool, const std::string&) { ++completions; });
+  Solver& base = solver;  // used through the reference's abstract interface
+  KokkosVector x = base.solve(KokkosVector());
+  dump("x.bin", x.data(), x.extent(0));
+  dump("rhs.bin", grid.get_rhs().data(), grid.get_rhs().extent(0));
+  MatrixFreeSystem system(n, n, lo, hi, lo, hi);
+  MatrixFreeSolver mf(system, system.get_rhs(), eps, max_it);
+  mf.enableMultigridPreconditioner(true);
+  std::vector<double> x2 = mf.solve(std::vector<double>());
+  dump("x_mf.bin", x2);
+  std::ofstream info(g_out + "/info.txt");
+  info.precision(17);
+  info << "iterations=" << base.getIterations() << "\nconverged=" << solver.hasConverged() << "\nlevels=" << solver.multigridLevels()
+       << "\nr0=" << solver.getInitialResidualNorm() << "\nr=" << solver.getFinalResidualNorm() << "\nname=" << base.getName()
+       << "\ncompletions=" << completions << "\nmf_iterations=" << mf.getIterations() << "\n";
+  return 0;
+}
+
 int cmd_grid(char** a) {
   const int n = std::atoi(a[0]);
   const double lo = std::atof(a[1]), hi = std::atof(a[2]);
@@ -269,7 +296,7 @@ int cmd_stop(char** a) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|grid|errors|io|stop> <args...> <outdir>\n");
+    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|grid|mgpcg|errors|io|stop> <args...> <outdir>\n");
     return 2;
   }
   g_out = argv[argc - 1];
@@ -278,6 +305,7 @@ int main(int argc, char** argv) {
     if (cmd == "dirichlet" && argc == 16) return cmd_dirichlet(argv + 2);
     if (cmd == "mf" && argc == 9) return cmd_mf(argv + 2);
     if (cmd == "grid" && argc == 10) return cmd_grid(argv + 2);
+    if (cmd == "mgpcg" && argc == 8) return cmd_mgpcg(argv + 2);
     if (cmd == "errors") return cmd_errors(argv + 2);
     if (cmd == "io" && argc == 3) return cmd_io(argv + 2);
     if (cmd == "stop" && argc == 4) return cmd_stop(argv + 2);

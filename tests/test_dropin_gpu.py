@@ -194,3 +194,26 @@ def test_request_stop_from_another_thread(driver, tmp_path):
     run(driver, "stop", 1024, tmp_path)
     i = info(tmp_path)
     assert i["stop_reason"] == "Прервано пользователем" and int(i["converged"]) == 0 and int(i["iterations"]) > 0
+
+
+@pytest.mark.gpu
+def test_multigrid_pcg_behind_the_solver_interface(driver, tmp_path, oracle_mod):
+    """The opt-in preconditioned CG as a Solver subclass on a GridSystem (solver.hpp:17-66 is the base class kept for
+    further solvers) and as a switch of MatrixFreeSolver: same solution as the reference-order plain CG, 7 iterations."""
+    from oracle import mg_oracle as mg
+
+    n = 128
+    run(driver, "mgpcg", n, 0, 1, 1e-8, 1000, tmp_path)
+    i = info(tmp_path)
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, 0)
+    b = o.rhs()
+    assert np.array_equal(f64(tmp_path, "rhs.bin"), b) or relmax(f64(tmp_path, "rhs.bin"), b) < 1e-14
+    ref = mg.MgPcg(n, n).solve(mg.to_grid(f64(tmp_path, "rhs.bin"), n, n, True), eps=1e-8, max_it=1000)
+    assert int(i["iterations"]) == ref["iterations"] == int(i["mf_iterations"]) and int(i["converged"]) == 1
+    assert int(i["levels"]) == ref["levels"] == 6 and int(i["completions"]) == 1
+    x = f64(tmp_path, "x.bin")
+    assert relmax(x, mg.from_grid(ref["x"], n, n, True)) < 1e-10
+    assert np.array_equal(x, f64(tmp_path, "x_mf.bin"))
+    plain = o.mf_solve(b=b, eps=1e-10, max_it=20000)
+    assert relmax(x, plain["x"]) < 1e-7
+    assert float(i["r"]) <= 1e-8 * float(i["r0"])
