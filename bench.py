@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-extras", "--no-single-sweep-extra", dest="no_extras", action="store_true",
                     help="skip the extra legs (two-sweep iteration on the same grid, assembled-CSR CG at 8192^2)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the in-run sharded parity cases")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the process to its GPU's NUMA node")
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--iters-per-graph", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -142,6 +143,31 @@ class ClockSampler:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Host side of the end-to-end number: run this process - and first-touch the pinned buffers it allocates next - on
+    the NUMA node its GPU hangs off, so that at N > 1 the ranks' H2D / D2H copies do not all cross the socket link.
+    Returns a short description (or why nothing was done)."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"bound": False, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": f"no allowed CPU on NUMA node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "gpu_pci": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception as exc:
+        return {"bound": False, "why": repr(exc)}
 
 
 def grid_side(n1, gpus, domain):
@@ -256,6 +282,7 @@ def run_b200(args):
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device - libb200cg has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     comm_id = None
     if world > 1:
         import torch.distributed as dist
@@ -368,7 +395,7 @@ def run_b200(args):
                "d2h_bytes_per_step": int(sum_over_ranks(float(n_local * 8))),
                "ms_per_step": e_wall / max(args.steps, 1), "device_ms_per_step": max_over_ranks(e_dev) / max(args.steps, 1),
                "timing": "host wall clock around the C-ABI calls, barrier + device synchronize on both sides",
-               "checksum": checksum}
+               "checksum": checksum, "host_numa_binding_rank0": numa}
         hb.free()
         hx.free()
 

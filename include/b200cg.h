@@ -235,6 +235,12 @@ int b200cg_postprocess(b200cg_plan_t plan, int op, double* residual_host, double
  * kernel flavour (0 = dot phase, 1 = update phase without x, 2 = update phase with x, 3 = single-sweep iteration). out receives 2 * (*n_ctas)
  * values; capacity is the number of pairs out can hold. */
 int b200cg_cta_times(b200cg_plan_t plan, int flavour, uint64_t* out, int capacity, int* n_ctas);
+/* Diagnostics of the sharded single-sweep iteration (plans created with B200CG_PEER_TRACE=1 in the environment): four
+ * device global-timer stamps (ns) per iteration, ring of 4096 iterations indexed by iteration % 4096 - this rank's sums
+ * ready (its sweep is over), published to every rank, every rank's flag seen, scalars formed. out receives 4 * (*n)
+ * values. The timers of different GPUs are not synchronised: scripts/peer_trace.py bounds their offsets from the
+ * stamps themselves. */
+int b200cg_peer_trace(b200cg_plan_t plan, uint64_t* out, int capacity, int* n_iterations);
 /* copy the device-resident solution of the last solve (keep_x_on_device) to the host */
 int b200cg_get_solution(b200cg_plan_t plan, double* x_host);
 

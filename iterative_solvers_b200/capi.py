@@ -23,7 +23,7 @@ EXPORTS = [
     "b200cg_partition", "b200cg_work_split",
     "b200cg_build_rhs", "b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_coords",
     "b200cg_apply", "b200cg_set_csr", "b200cg_assemble_csr", "b200cg_get_csr", "b200cg_csr_apply",
-    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times",
+    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times", "b200cg_peer_trace",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
         L.b200cg_comm_unique_id.argtypes = [C.c_void_p]
         L.b200cg_device_count.argtypes = [C.POINTER(C.c_int)]
         L.b200cg_cta_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.b200cg_peer_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -309,6 +310,14 @@ class Plan:
         n = C.c_int()
         check(self.L.b200cg_cta_times(self.h, int(flavour), _ptr(buf), cap, C.byref(n)))
         return buf[: 2 * n.value].reshape(-1, 2).astype(np.int64)
+
+    def peer_trace(self):
+        """[4096, 4] global-timer stamps of the sharded single sweep's cross-rank step (plans created with
+        B200CG_PEER_TRACE=1): sums ready, published, all flags seen, scalars formed; row = iteration % 4096."""
+        buf = np.zeros(4 * 4096, dtype=np.uint64)
+        n = C.c_int()
+        check(self.L.b200cg_peer_trace(self.h, _ptr(buf), 4096, C.byref(n)))
+        return buf[: 4 * n.value].reshape(-1, 4).astype(np.int64)
 
     def postprocess(self, op=OP_MATRIX_FREE, want_residual=True, want_error=True):
         res = np.empty(self.n_local) if want_residual else None

@@ -218,54 +218,31 @@ static __global__ void __launch_bounds__(CTA_THREADS) csr_init_kernel(const CsrA
 }
 
 // CG = 0: Az = A z_old (plain SpMV, b200cg_csr_apply).  CG = 1: the fused direction update + SpMV + dots.
-// One thread per row, but the matrix is read warp-cooperatively: the non-zeros of a warp's 32 consecutive rows are
-// contiguous in values / entries (160 of them for the 5-point matrix), so the warp copies them into shared memory
-// with fully coalesced loads and every lane then walks its own row there. (One thread reading its row straight from
-// global memory touches values at a 40-byte lane stride - five partially used sectors per request; ncu showed that
-// kernel waiting on the load pipe at 68 % of the DRAM peak: profiles/r2_ncu_full_summary_csr_8192.txt.) Rows too long
-// for the staging buffer (a general matrix from b200cg_set_csr) fall back to the direct walk.
-constexpr int CSR_STAGE = 224;  // non-zeros staged per warp (32 rows x 5 = 160 for this matrix; 7 per row fit)
+// One thread per row walking its row in global memory. The 40-byte lane stride looks wasteful, but the L1 absorbs it:
+// DRAM traffic is 4.87 GB per launch at 8192^2 against 5.23 GB of model bytes and the kernel runs at 0.86 of the measured
+// copy peak. A warp-cooperative variant (the warp's 160 non-zeros copied into shared memory with coalesced loads, lanes
+// walking their rows there) was measured and was 34 % SLOWER (1.25 ms against 0.93 ms per launch, profiles/r2_csr.md).
 template <int CG>
 static __global__ void __launch_bounds__(CTA_THREADS) csr_spmv_kernel(const CsrArgs a) {
   __shared__ double scratch[2 * 32];
-  __shared__ double s_val[CTA_THREADS / 32][CSR_STAGE];
-  __shared__ int s_col[CTA_THREADS / 32][CSR_STAGE];
   DevState* st = a.st;
   double beta = 0.0;
   if (CG) {
     if (st->done) return;
     beta = st->beta;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s[2] = {0.0, 0.0}, mx[1] = {0.0};
-  // (whole warps iterate together: the loop bound is per warp)
-  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < a.nrows;
-       i0 += (long long)gridDim.x * blockDim.x) {
-    const long long i = i0 + lane;
-    const bool row_ok = i < a.nrows;
-    const int k0 = a.row_map[row_ok ? i : a.nrows], k1 = a.row_map[row_ok ? i + 1 : a.nrows];
-    const int kb = __shfl_sync(0xffffffffu, k0, 0);
-    const long long last = (i0 + 32 < a.nrows ? i0 + 32 : a.nrows);
-    const int ke = a.row_map[last];
-    const bool staged = (ke - kb) <= CSR_STAGE;
-    if (staged) {
-      for (int k = kb + lane; k < ke; k += 32) {
-        s_val[warp][k - kb] = a.values[k];
-        s_col[warp][k - kb] = a.entries[k];
-      }
-    }
-    __syncwarp();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrows;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k0 = a.row_map[i], k1 = a.row_map[i + 1];
     double sum = 0.0;
     for (int k = k0; k < k1; ++k) {
-      const int c = staged ? s_col[warp][k - kb] : a.entries[k];
-      const double v = staged ? s_val[warp][k - kb] : a.values[k];
+      const int c = a.entries[k];
       double zc;
       if (CG) zc = __dadd_rn(a.r[c], __dmul_rn(beta, a.z_old[c]));  // z = r + beta z, msg_solver.cpp:167-169
       else zc = a.z_old[c];
-      sum = __dadd_rn(sum, __dmul_rn(v, zc));
+      sum = __dadd_rn(sum, __dmul_rn(a.values[k], zc));
     }
-    __syncwarp();  // the staging buffer is rewritten by the next round
-    if (!row_ok) continue;
     a.Az[i] = sum;  // alpha = 1, beta = 0: y = 1.0 * sum
     if (CG) {
       const double ri = a.r[i];

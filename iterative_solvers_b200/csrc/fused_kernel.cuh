@@ -342,10 +342,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
     // rank's next publication cannot overwrite values a slow rank is still reading
     const int phase = X2 ? 1 : 0;
     double mine[2] = {gamma, delta}, none[1] = {0.0}, total[4];
+    unsigned long long* tr = a.peer_trace ? a.peer_trace + 4 * (size_t)(st->it % PEER_TRACE_CAP) : nullptr;
+    if (tr) tr[0] = global_ns();
     peer_publish<2, 0>(a.peers, st, phase, mine, none, stop_req);
+    if (tr) tr[1] = global_ns();
     if (!peer_collect(st, a.peers, phase, total, &stop_req)) return;
+    if (tr) tr[2] = global_ns();
     gamma = total[0];
     delta = total[1];
+    finalize_fused(st, gamma, delta, FLAGS);
+    apply_stop(st, stop_req);
+    if (tr) tr[3] = global_ns();
+    return;
   }
   finalize_fused(st, gamma, delta, FLAGS);
   apply_stop(st, stop_req);

@@ -55,6 +55,8 @@ struct TileArgs {
   double* nb_p_above2;
   unsigned long long* cta_clock;  // [2 * gridDim.x] globaltimer at CTA start / end of its sweep (load balancing)
   const int* stop_flag;  // mapped host flag (requestStop, msg_solver.cpp:82), polled every STOP_POLL_EVERY-th iteration
+  unsigned long long* peer_trace;  // diagnostics (B200CG_PEER_TRACE=1): [PEER_TRACE_CAP][4] globaltimer stamps of the
+                                   // single sweep's cross-rank step - local sums ready, published, all flags seen, scalars formed
   Geom g;
 };
 
@@ -171,6 +173,7 @@ __device__ __forceinline__ void append_record(DevState* st, CbRecord* log, doubl
 // iterations instead of at the next graph boundary. Call before st->it is advanced; on a sharded plan every rank
 // looks at the same iterations and the maximum over the ranks decides, so all ranks stop together.
 constexpr int STOP_POLL_EVERY = 16;
+constexpr int PEER_TRACE_CAP = 4096;  // iterations kept by the peer-exchange trace (ring)
 __device__ __forceinline__ bool poll_stop(const DevState* st, const int* stop_flag) {
   if (!stop_flag || ((st->it + 1) % STOP_POLL_EVERY) != 0) return false;
   return *reinterpret_cast<const volatile int*>(stop_flag) != 0;

@@ -348,6 +348,10 @@ static int setup_peer_memory(b200cg_plan_s* P) {
   bool all_ok = false;
   if (!comm_all_agree(&P->comm, mine, &all_ok, P->stream, &err)) return fail(B200CG_ERR_COMM, "%s", err.c_str());
   P->peer_mode = all_ok;
+  if (all_ok && getenv("B200CG_PEER_TRACE") && atoi(getenv("B200CG_PEER_TRACE")) != 0) {
+    CU(cudaMalloc(&P->d_peer_trace, sizeof(unsigned long long) * 4 * PEER_TRACE_CAP));
+    CU(cudaMemset(P->d_peer_trace, 0, sizeof(unsigned long long) * 4 * PEER_TRACE_CAP));
+  }
   if (all_ok) {
     CU(cudaMalloc(&P->d_links, sizeof(PeerLinks)));
     CU(cudaMemcpy(P->d_links, &links, sizeof(links), cudaMemcpyHostToDevice));
@@ -364,6 +368,7 @@ static void free_plan(b200cg_plan_s* P) {
   for (void* q : P->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(P->d_sync);
   cudaFree(P->d_links);
+  cudaFree(P->d_peer_trace);
   comm_destroy(&P->comm);
   csr_free(&P->csr);
   mg_free(P);
@@ -733,6 +738,17 @@ extern "C" int b200cg_csr_apply(b200cg_plan_t P, const double* x_host, double* y
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(y_host, P->csr.Az, N * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
   CU(cudaStreamSynchronize(P->stream));
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_peer_trace(b200cg_plan_t P, uint64_t* out, int capacity, int* n_iterations) {
+  if (!P || !out || !n_iterations) return fail(B200CG_ERR_INVALID_ARG, "plan/out/n_iterations is NULL");
+  *n_iterations = 0;
+  if (!P->d_peer_trace) return fail(B200CG_ERR_STATE, "no peer-exchange trace: create the sharded plan with B200CG_PEER_TRACE=1");
+  const int n = std::min(capacity, PEER_TRACE_CAP);
+  CU(cudaSetDevice(P->desc.device));
+  CU(cudaMemcpy(out, P->d_peer_trace, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  *n_iterations = n;
   return B200CG_OK;
 }
 

@@ -127,6 +127,7 @@ struct b200cg_plan_s {
   double* nb_above_r[2] = {nullptr, nullptr};
   double* nb_above_p[2] = {nullptr, nullptr};
   unsigned long long peer_epoch[2] = {0, 0};
+  unsigned long long* d_peer_trace = nullptr;  // B200CG_PEER_TRACE=1: stamps of the single sweep's cross-rank step
   int64_t n_global = 0;
   std::vector<int> ycuts;  // row cuts of all ranks
   MgHierarchy* mg = nullptr;  // level hierarchy of the opt-in multigrid preconditioner (built by the first solve that asks)

@@ -64,6 +64,7 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     if (peer) {
       a.defer = 2;
       a.peers = P->d_links;
+      a.peer_trace = P->d_peer_trace;
       const Geom& g = P->g;
       const int rank = P->desc.rank;
       if (rank > 0) {  // neighbour below: its top halo row is its last stored row

