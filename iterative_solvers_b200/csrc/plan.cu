@@ -389,6 +389,11 @@ static void free_plan(b200cg_plan_s* P) {
     cudaFree(tt.d_tiles);
     cudaFree(tt.d_cta_begin);
   }
+  for (int k = 0; k < 2; ++k) {
+    if (P->h_state_m[k]) cudaFreeHost(P->h_state_m[k]);
+    if (P->h_log_m[k]) cudaFreeHost(P->h_log_m[k]);
+    if (P->ev_launch[k]) cudaEventDestroy(P->ev_launch[k]);
+  }
   if (P->h_state) cudaFreeHost(P->h_state);
   if (P->h_log) cudaFreeHost(P->h_log);
   if (P->h_stop) cudaFreeHost(P->h_stop);
@@ -440,6 +445,11 @@ static int plan_create_impl(b200cg_plan_s* P) {
   memset(P->h_state, 0, sizeof(DevState));
   CU(cudaMalloc(&P->d_log, sizeof(CbRecord) * CB_LOG_CAP));
   CU(cudaHostAlloc(&P->h_log, sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
+  for (int k = 0; k < 2; ++k) {
+    CU(cudaHostAlloc(&P->h_state_m[k], sizeof(DevState), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&P->h_log_m[k], sizeof(CbRecord) * CB_LOG_CAP, cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&P->ev_launch[k], cudaEventDisableTiming));
+  }
   for (auto& c : P->d_clock) {
     CU(cudaMalloc(&c, sizeof(unsigned long long) * 2 * (size_t)P->sms * 3));
     CU(cudaMemsetAsync(c, 0, sizeof(unsigned long long) * 2 * (size_t)P->sms * 3, P->stream));

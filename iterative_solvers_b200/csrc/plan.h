@@ -54,7 +54,7 @@ double now_ms();
 
 // ------------------------------------------------------------------------------------------- plan
 // Graph variants (key of b200cg_plan_s::graphs = variant * 4096 + iterations per graph)
-enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16 };
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16, V_TIMED = 32 };
 
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
@@ -101,7 +101,10 @@ struct b200cg_plan_s {
   double* vb = nullptr;
   double* compact = nullptr;  // staging buffer in the reference's compact ordering (local range)
   DevState* d_state = nullptr;
-  DevState* h_state = nullptr;  // pinned mirror
+  DevState* h_state = nullptr;  // pinned mirror (the canonical copy the solve's tail reads)
+  DevState* h_state_m[2] = {nullptr, nullptr};  // the graph loop's two read-back targets (launches are pipelined)
+  CbRecord* h_log_m[2] = {nullptr, nullptr};
+  cudaEvent_t ev_launch[2] = {};                // read-back of launch slot k complete
   CbRecord* d_log = nullptr;
   CbRecord* h_log = nullptr;  // pinned mirror
   int* h_stop = nullptr;      // mapped flag the cluster kernel polls (interrupt requests)

@@ -22,31 +22,40 @@ extern "C" int b200cg_apply(b200cg_plan_t P, const double* x_host, double* y_hos
 }
 
 // ------------------------------------------------------------------------------------------- solve
-// Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) plus the status
-// read-back into one executable graph. Event-record nodes bracket the kernels of the first iteration.
-static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out) {
+// Captures `iters` CG iterations (even, so the ping-pong buffers return to their start) into one executable graph.
+// timed: event-record nodes bracket the kernels of the first two iterations (the variant a solve launches first; the
+// launches after it are pipelined and must not re-record events the host is still reading).
+// Event nodes bracket iterations 2 and 3 of a timed graph (0 and 1 of a very short one): the first iteration of a
+// launch still carries the launch skew between the ranks of a sharded plan.
+static int timed_first_iteration(int iters) { return iters >= 4 ? 2 : 0; }
+
+static int build_graph(b200cg_plan_s* P, int variant, int iters, bool timed, GraphEntry* out) {
   cudaStream_t s = P->stream;
   const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR, xdefer = variant & V_XDEFER;
   const bool fused = variant & V_FUSED;
   int kernels = 0;
+  const int k0 = timed_first_iteration(iters);  // the two iterations whose kernels are bracketed by event nodes
+  auto EV = [&](cudaEvent_t e, cudaStream_t st, unsigned int flags) {
+    if (timed) cudaEventRecordWithFlags(e, st, flags);
+  };
   CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200CG_OK;
   for (int k = 0; k < iters && rc == B200CG_OK; ++k) {
     const int par = k & 1;
-    if (k == 0) cudaEventRecordWithFlags(P->ev[0], s, cudaEventRecordExternal);
+    if (k == k0) EV(P->ev[0], s, cudaEventRecordExternal);
     if (csr) {
       // assembled path: p update + SpMV + dots, then the shared update pass
       CsrArgs ca = csr_args(&P->csr, P->d_state, P->d_partials, P->d_log, par);
       ca.stop_flag = P->d_stop;
       csr_spmv_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       ++kernels;
-      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
+      if (k == k0) EV(P->ev[1], s, cudaEventRecordExternal);
       if (with_u)
         csr_update_kernel<1><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       else
         csr_update_kernel<0><<<csr_grid(P->csr.nrows, P->sms), CTA_THREADS, 0, s>>>(ca);
       ++kernels;
-      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
+      if (k == k0) EV(P->ev[2], s, cudaEventRecordExternal);
       continue;
     }
     TileArgs a = base_args(P);
@@ -85,12 +94,12 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
     if (fused) {
       // single-sweep iteration: one kernel; x touched on odd iterations only (the event slots of the absent dot
       // phase collapse to zero length)
-      if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
-      if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
+      if (k == k0) EV(P->ev[1], s, cudaEventRecordExternal);
+      if (k == k0 + 1) EV(P->ev[8], s, cudaEventRecordExternal);
       rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
       ++kernels;
-      if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
-      if (k == 1) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
+      if (k == k0) EV(P->ev[2], s, cudaEventRecordExternal);
+      if (k == k0 + 1) EV(P->ev[9], s, cudaEventRecordExternal);
       continue;
     }
     rc = launch_tile<MODE_DOT, 0>(P, a, s);
@@ -99,8 +108,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       rc = reduce_and_finalize(P, 1, fl, false, s);
       ++kernels;
     }
-    if (k == 0) cudaEventRecordWithFlags(P->ev[1], s, cudaEventRecordExternal);
-    if (k == 1) cudaEventRecordWithFlags(P->ev[8], s, cudaEventRecordExternal);
+    if (k == k0) EV(P->ev[1], s, cudaEventRecordExternal);
+    if (k == k0 + 1) EV(P->ev[8], s, cudaEventRecordExternal);
     if (rc != B200CG_OK) break;
     if (xdefer) rc = (k & 1) ? launch_tile<MODE_UPD, F_X2>(P, a, s) : launch_tile<MODE_UPD, F_NOX>(P, a, s);
     else if (report && with_u) rc = launch_tile<MODE_UPD, F_REPORT | F_U>(P, a, s);
@@ -113,8 +122,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       ++kernels;
       if (rc == B200CG_OK) rc = exchange_halo2(P, P->r[par ^ 1], P->p[par ^ 1]);
     }
-    if (k == 0) cudaEventRecordWithFlags(P->ev[2], s, cudaEventRecordExternal);
-    if (k == 1 && !report) cudaEventRecordWithFlags(P->ev[9], s, cudaEventRecordExternal);
+    if (k == k0) EV(P->ev[2], s, cudaEventRecordExternal);
+    if (k == k0 + 1 && !report) EV(P->ev[9], s, cudaEventRecordExternal);
     if (rc == B200CG_OK && report) {
       TileArgs ra = base_args(P);
       ra.p_in = P->x;
@@ -131,8 +140,6 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, GraphEntry* out
       }
     }
   }
-  cudaMemcpyAsync(P->h_state, P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(P->h_log, P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s);
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   if (rc != B200CG_OK) {
@@ -200,11 +207,12 @@ static int launch_cluster_solve(b200cg_plan_s* P, int ctas, int rows_per_cta, si
 }
 
 static int default_iters_per_graph(const b200cg_plan_s* P) {
-  // small grids are launch-bound: long graphs; big grids: keep the stop/interrupt latency around 0.1 s
-  const long long n = local_count(P);
-  if (n <= (1LL << 20)) return 100;
-  if (n <= (1LL << 24)) return 50;
-  return 20;
+  // A launch should last ~50 ms: every graph boundary costs a host round trip (~0.1 ms on one GPU, ~0.4 ms as the
+  // maximum over 8 ranks - profiles/r2_scaling.md) even though consecutive launches are pipelined, and nothing else
+  // depends on the length any more (interrupts are polled on the device, callback records are logged there).
+  const double t_it_us = 15.0 + (double)local_count(P) * 40.0 / 5.5e6;  // 40 B per unknown at 5.5 TB/s + fixed cost
+  const int k = (int)(50e3 / t_it_us);
+  return std::max(20, std::min(200, k & ~1));
 }
 
 // Everything one b200cg_solve call carries between its phases.
@@ -303,13 +311,12 @@ static int arm_device_state(SolveCall& c) {
   return B200CG_OK;
 }
 
-static void deliver_callbacks(SolveCall& c) {
-  const DevState& st = *c.P->h_state;
+static void deliver_callbacks(SolveCall& c, const DevState& st, const CbRecord* log) {
   if (c.cb) {
     // (the launch sizes keep a launch's records within the ring; should one ever lap it, deliver the surviving tail only)
     if (st.n_log - c.consumed > (unsigned int)CB_LOG_CAP) c.consumed = st.n_log - CB_LOG_CAP;
     for (; c.consumed < st.n_log; ++c.consumed) {
-      const CbRecord& rec = c.P->h_log[c.consumed % CB_LOG_CAP];
+      const CbRecord& rec = log[c.consumed % CB_LOG_CAP];
       c.cb(c.user, (int)rec.it, rec.precision, rec.residual, rec.error);
     }
   } else {
@@ -335,7 +342,7 @@ static int run_cluster_solve(SolveCall& c, int ctas, int rows_per_cta, size_t sm
   }
   CU(cudaStreamSynchronize(s));
   c.interrupted = P->h_state->stop_reason == B200CG_STOP_INTERRUPTED;
-  deliver_callbacks(c);
+  deliver_callbacks(c, *P->h_state, P->h_log);
   return B200CG_OK;
 }
 
@@ -397,7 +404,8 @@ static int launch_init(SolveCall& c) {
 
 // Event nodes bracket the kernels of the first two captured iterations of a graph launch; a sample counts only if
 // those iterations really ran in this launch (`advanced` = iterations completed by it).
-static void sample_kernel_times(SolveCall& c, int advanced) {
+static void sample_kernel_times(SolveCall& c, int advanced, int K) {
+  advanced -= timed_first_iteration(K);  // iterations completed from the first bracketed one on
   b200cg_plan_s* P = c.P;
   float d0 = 0.f, u0 = 0.f, d1 = 0.f, u1 = 0.f;
   if (!c.csr && !c.report && advanced >= 2) {
@@ -443,38 +451,65 @@ static int run_graph_solve(SolveCall& c) {
   c.xdefer = c.fused || (P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2);
   const int variant = c.fused ? V_FUSED
                               : (c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0)));
-  GraphEntry& ge = P->graphs[variant * 4096 + K];
-  if (!ge.exec) RET(build_graph(P, variant, K, &ge));
+  // two cached graphs per (variant, K): with event nodes (first launch of a solve: kernel times) and without
+  GraphEntry& g_timed = P->graphs[(variant | V_TIMED) * 4096 + K];
+  GraphEntry& g_plain = P->graphs[variant * 4096 + K];
+  if (!g_timed.exec) RET(build_graph(P, variant, K, true, &g_timed));
+  if (!g_plain.exec) RET(build_graph(P, variant, K, false, &g_plain));
 
   CU(cudaEventRecord(P->ev[5], s));
-  int it_before = 0;
   *P->h_stop = 0;
   // Interrupts (requestStop): the caller's flag is forwarded into the mapped flag the loop kernels poll every
   // STOP_POLL_EVERY-th iteration; the device then ends the solve with INTERRUPTED - on a sharded peer-memory plan on
   // every rank at the same iteration (the request travels with the reduction slots). Only the NCCL exchange (fallback,
   // per-iteration report) lacks that channel: there the ranks agree between graph launches.
   const bool device_stop = P->desc.world <= 1 || (P->peer_mode && !c.report);
-  // the init kernel's verdict (0 iterations) and its callback record come back with the first graph launch
-  for (;;) {
+  // Launches are pipelined: launch k+1 is enqueued before the host waits for launch k's read-back (two pinned mirrors),
+  // so the GPU never idles across a graph boundary and the ranks of a sharded plan do not pick up each other's host
+  // jitter. A launch enqueued after the stop rule fired drains harmlessly (kernels begin with `if (st->done) return`).
+  // Not pipelined: the solve's first launch (its event nodes are read), launches followed by a feedback-balancing
+  // step (needs an idle stream), and the NCCL exchange (the ranks agree on stop requests between launches).
+  int last_slot = 0;  // read-back target of the most recently enqueued launch
+  auto enqueue = [&](int slot, GraphEntry& ge) -> int {
+    last_slot = slot;
     if (c.stop_flag && *c.stop_flag) *P->h_stop = 1;
     CU(cudaGraphLaunch(ge.exec, s));
     c.info->kernel_launches += ge.kernels;
+    CU(cudaMemcpyAsync(P->h_state_m[slot], P->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(P->h_log_m[slot], P->d_log, sizeof(CbRecord) * CB_LOG_CAP, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(P->ev_launch[slot], s));
+    return B200CG_OK;
+  };
+  auto wait_for = [&](int slot) -> int {
     if (c.stop_flag) {
-      CU(cudaEventRecord(P->ev[10], s));
-      for (int spins = 0; cudaEventQuery(P->ev[10]) == cudaErrorNotReady; ++spins) {
+      for (int spins = 0; cudaEventQuery(P->ev_launch[slot]) == cudaErrorNotReady; ++spins) {
         if (*c.stop_flag) *P->h_stop = 1;
         if (spins > 20000) std::this_thread::sleep_for(std::chrono::microseconds(20));
       }
     }
-    CU(cudaStreamSynchronize(s));
-    const DevState& st = *P->h_state;
+    CU(cudaEventSynchronize(P->ev_launch[slot]));
+    return B200CG_OK;
+  };
+  int& rounds = c.fused ? P->balance_rounds_fused : P->balance_rounds;
+  int it_before = 0, cur = 0;
+  bool next_enqueued = false;
+  // the init kernel's verdict (0 iterations) and its callback record come back with the first launch
+  RET(enqueue(cur, g_timed));
+  for (bool first = true;; first = false) {
+    const bool balancing = rounds > 0 && !c.csr;
+    const bool pipelined = !first && !balancing && device_stop;
+    if (pipelined && !next_enqueued) {
+      RET(enqueue(cur ^ 1, g_plain));
+      next_enqueued = true;
+    }
+    RET(wait_for(cur));
+    const DevState& st = *P->h_state_m[cur];
     const int advanced = st.it - it_before;
     it_before = st.it;
-    sample_kernel_times(c, advanced);
-    deliver_callbacks(c);
+    if (first) sample_kernel_times(c, advanced, K);
+    deliver_callbacks(c, st, P->h_log_m[cur]);
     if (st.done) break;
-    int& rounds = c.fused ? P->balance_rounds_fused : P->balance_rounds;
-    if (rounds > 0 && !c.csr && advanced >= 2) {
+    if (balancing && advanced >= 2) {
       // young plan: correct the static split from the measured per-CTA sweep times (the stream is idle here); only
       // the flavours this loop launches carry fresh stamps
       if (c.fused) {
@@ -498,7 +533,15 @@ static int run_graph_solve(SolveCall& c) {
       c.interrupted = true;
       break;
     }
+    if (!next_enqueued) RET(enqueue(cur ^ 1, g_plain));
+    next_enqueued = false;
+    cur ^= 1;
   }
+  // A launch enqueued ahead drains: after the stop rule fired it does nothing; after a host-side interrupt it may have
+  // advanced a few more iterations (until the device saw the flag) - either way its read-back is the final state.
+  CU(cudaStreamSynchronize(s));
+  deliver_callbacks(c, *P->h_state_m[last_slot], P->h_log_m[last_slot]);
+  *P->h_state = *P->h_state_m[last_slot];
   if (P->h_state->stop_reason == B200CG_STOP_INTERRUPTED) c.interrupted = true;
   return B200CG_OK;
 }

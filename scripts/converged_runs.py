@@ -2,8 +2,8 @@
 """Converged solves on record (loop condition of MatrixFreeSolver::solve, matrix_free_system.cpp:409: relative
 recurrence residual <= eps): iterations, seconds, final ||r||/||r0||, the TRUE residual ||b - A x||/||b|| recomputed by
 b200cg_postprocess, max|x - u| against the analytic solution (expected O(h^2)), for the plain CG iteration(s) and the
-opt-in multigrid-preconditioned one. One GPU:  python scripts/converged_runs.py --n 4096 [--eps 1e-8]
-N GPUs (row slabs): python -m torch.distributed.run --nproc-per-node N ... scripts/converged_runs.py --n 16384
+opt-in multigrid-preconditioned one. One GPU:  python scripts/converged_runs.py --grid-n 4096 [--eps 1e-8]
+N GPUs (row slabs): python -m torch.distributed.run --nproc-per-node N ... scripts/converged_runs.py --grid-n 16384
 Prints one JSON line per solve."""
 import argparse
 import json
@@ -20,7 +20,7 @@ from iterative_solvers_b200 import capi  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--grid-n", dest="n", type=int, default=4096)
     ap.add_argument("--eps", type=float, default=1e-8)
     ap.add_argument("--max-it", type=int, default=200000)
     ap.add_argument("--modes", default="single_sweep,two_sweep,multigrid")

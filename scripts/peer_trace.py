@@ -9,7 +9,7 @@ publish -> all flags seen -> scalars formed on every rank (b200cg_peer_trace), s
 The GPUs' timers are not synchronised; their offsets are bounded from the stamps themselves (rank r sees rank 0's flag
 after it was published and vice versa) and the midpoint is used; the half-width is reported as the uncertainty.
 Run: B200CG_PEER_TRACE=1 python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/peer_trace.py
-     [--n 16384] [--iters 2000]   (strong scaling: the n x n grid sharded over all ranks). Prints one JSON line."""
+     [--grid-n 16384] [--iters 2000]   (strong scaling: the n x n grid sharded over all ranks). Prints one JSON line."""
 import argparse
 import json
 import os
@@ -27,7 +27,7 @@ from iterative_solvers_b200 import capi  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--grid-n", dest="n", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=2000)
     args = ap.parse_args()
     rank, local, world = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ["WORLD_SIZE"])
