@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
     double2 r1 = zero2, x1 = zero2, q1 = zero2;  // staged r, x, p_old of row y-1 (masked)
     bool k1a = false, k1b = false;         // row y-1: are this thread's two nodes unknowns
     bool va = false, vb = false;           // the same for the rows of the tile itself (all in one block of the L)
+    bool warp_on = true;                   // this warp writes at least one unknown of the tile
 
     for (;;) {
       mbar_wait(&full[stage], phase);
@@ -218,6 +219,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
         k1a = k1b = false;
         va = (x0 >= m.xlo) && (x0 <= g.n - 1);
         vb = (x0 + 1 >= m.xlo) && (x0 + 1 <= g.n - 1);
+        // A warp's results depend on its own 64-column window only, so a warp none of whose written columns
+        // (window columns 2 .. 61) is an unknown of this tile has nothing to do: it only hands the stages back. That
+        // is 6 of 7 warps in a last strip of a few columns (16383 = 39 x 420 + 3) and the left warps of the strip the
+        // re-entrant edge of the L cuts.
+        const int xw = m.col0 + FUSED_WARP_STEP * warp - XOFF;  // node of the window's first staged column
+        warp_on = (xw + 61 >= m.xlo) && (xw + 2 <= g.n - 1);
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
       // One staged row. full_tag: every row of the stage lies in [ya+2, yb), so it is stored, it is a row of the
@@ -318,7 +325,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
         k1a = k0a;  k1b = k0b;
       };
       // (sharded plans: the emit rows ya+1 and yb-2 may be rows the neighbours need, so FULL stays clear of them)
-      if (m.nrows == HS && m.y0 >= ya + (SHARD ? 3 : 2) && m.y0 + HS <= yb - (SHARD ? 1 : 0)) {
+      if (!warp_on) {
+        // nothing to compute for this tile
+      } else if (m.nrows == HS && m.y0 >= ya + (SHARD ? 3 : 2) && m.y0 + HS <= yb - (SHARD ? 1 : 0)) {
 #pragma unroll
         for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
       } else {

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
     uint32_t phase = 0;
     // per-tile state
     bool v0 = false, v1 = false;
+    bool warp_on = true;  // some column of this warp is an unknown of the tile
     int ya = 0;
     size_t eoff = 0;
     double2 pm = make_double2(0.0, 0.0), pc = make_double2(0.0, 0.0);
@@ -213,6 +214,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
         ya = m.ya;
         eoff = (size_t)(ya - g.ybase) * pitch + (size_t)(m.col0 + c2);
         pm = pc = make_double2(0.0, 0.0);
+        // a warp's results depend on its own 64 columns (and staged neighbours) only: a warp without a single unknown
+        // in this tile - the right half of a half-empty last strip, the columns left of the L's re-entrant edge - only
+        // hands the stages back
+        warp_on = __any_sync(0xffffffffu, v0 || v1);
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
       // One staged row. full_tag: every row of the stage is an interior row of its tile (emit always, x and u
@@ -363,7 +368,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
       };
       // FULL: rows y0 .. y0+HS-1 all in [ya, yb) and the emitted rows y0-1 .. y0+HS-2 all in (ya, yb-1), so neither
       // the tile's first emit row (a slab's first row goes to the neighbour's halo) nor its last is handled here
-      if (m.nrows == HS && !(m.flags & META_TILE_FIRST) && m.y0 - 1 > m.ya && m.y0 + HS <= m.yb) {
+      if (!warp_on) {
+        // nothing to compute for this tile
+      } else if (m.nrows == HS && !(m.flags & META_TILE_FIRST) && m.y0 - 1 > m.ya && m.y0 + HS <= m.yb) {
 #pragma unroll
         for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
       } else {
