@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
     bool k1a = false, k1b = false;         // row y-1: are this thread's two nodes unknowns
     bool va = false, vb = false;           // the same for the rows of the tile itself (all in one block of the L)
     bool warp_on = true;                   // this warp writes at least one unknown of the tile
+    bool st_ok = false;                    // this thread stores in the tile's rows (a writer lane with an unknown)
 
     for (;;) {
       mbar_wait(&full[stage], phase);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
         // re-entrant edge of the L cuts.
         const int xw = m.col0 + FUSED_WARP_STEP * warp - XOFF;  // node of the window's first staged column
         warp_on = (xw + 61 >= m.xlo) && (xw + 2 <= g.n - 1);
+        st_ok = writer && (va || vb);
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
       // One staged row. full_tag: every row of the stage lies in [ya+2, yb), so it is stored, it is a row of the
@@ -324,12 +326,64 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileAr
         r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
         k1a = k0a;  k1b = k0b;
       };
+      // The same row for a FULL stage (all but a tile's first and last), written branch-free: the ncu source page of the
+      // generic form showed 8 BRA + 5.5 BSYNC per warp-row from the lane-divergent `writer` regions and 10 % of the
+      // samples in branch resolution, in a kernel that waits for data only 12 % of the time (even flavour). Every lane
+      // computes everything; lanes 0 / 31 (and columns that are no unknowns) are taken out with selects on the two sums
+      // and a predicate on the stores. Same operations on the same values in the same order as do_row: bit-identical.
+      double2 G1 = zero2;  // r' of row y-2 as it enters the sums: zero in the lanes that do not write
+      size_t eo = 0;       // offset of the row being emitted
+      auto do_row_full = [&](const int j) {
+        const double2 cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
+        const double2 cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
+        double2 cur_x = zero2;
+        if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+        double2 P0;
+        P0.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
+        P0.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
+        const double LP0 = __shfl_up_sync(0xffffffffu, P0.y, 1);
+        const double RP0 = __shfl_down_sync(0xffffffffu, P0.x, 1);
+        const double ap0 = stencil(P1.x, LP1, P1.y, P0.x, P2.x);
+        const double ap1 = stencil(P1.y, P1.x, RP1, P0.y, P2.y);
+        double2 R0;
+        R0.x = va ? __dsub_rn(r1.x, __dmul_rn(alpha, ap0)) : 0.0;
+        R0.y = vb ? __dsub_rn(r1.y, __dmul_rn(alpha, ap1)) : 0.0;
+        double2 xn = zero2;
+        if (X2) {  // x += alpha_prev * p_old, then += alpha * p: the reference's order of additions
+          xn.x = __dadd_rn(__dadd_rn(x1.x, __dmul_rn(alpha_prev, q1.x)), __dmul_rn(alpha, P1.x));
+          xn.y = __dadd_rn(__dadd_rn(x1.y, __dmul_rn(alpha_prev, q1.y)), __dmul_rn(alpha, P1.y));
+        }
+        st2_out_if(st_ok, a.r_out + eo, R0);
+        st2_out_if(st_ok, a.p_out + eo, P1);
+        if (X2) st2_out_if(st_ok, a.x + eo, xn);
+        eo += pitch;
+        const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
+        const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
+        const double w0 = stencil(R1.x, LR1, R1.y, R0.x, R2.x);
+        const double w1 = stencil(R1.y, R1.x, RR1, R0.y, R2.y);
+        double2 G0;
+        G0.x = writer ? R0.x : 0.0;
+        G0.y = writer ? R0.y : 0.0;
+        acc_s[0] = fma(G0.x, G0.x, acc_s[0]);
+        acc_s[0] = fma(G0.y, G0.y, acc_s[0]);
+        acc_s[1] = fma(G1.x, w0, acc_s[1]);
+        acc_s[1] = fma(G1.y, w1, acc_s[1]);
+        G1 = G0;
+        R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
+        P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
+        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
+      };
       // (sharded plans: the emit rows ya+1 and yb-2 may be rows the neighbours need, so FULL stays clear of them)
       if (!warp_on) {
         // nothing to compute for this tile
       } else if (m.nrows == HS && m.y0 >= ya + (SHARD ? 3 : 2) && m.y0 + HS <= yb - (SHARD ? 1 : 0)) {
+        G1.x = writer ? R1.x : 0.0;
+        G1.y = writer ? R1.y : 0.0;
+        eo = (size_t)(m.y0 - 1 - g.ybase) * pitch + col_off;
 #pragma unroll
-        for (int j = 0; j < HS; ++j) do_row(j, cuda::std::true_type{});
+        for (int j = 0; j < HS; ++j) do_row_full(j);
+        k1a = va;  // (what the generic form would have left behind)
+        k1b = vb;
       } else {
 #pragma unroll 1
         for (int j = 0; j < m.nrows; ++j) do_row(j, cuda::std::false_type{});

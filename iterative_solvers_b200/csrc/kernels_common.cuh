@@ -78,6 +78,19 @@ __device__ __forceinline__ void st2_out(double* p, double2 v) {
 #endif
 }
 
+// The same store under a predicate, without a branch (the compiler wraps a conditional group of 16-byte stores in a
+// divergent region: BSSY / BRA / BSYNC per row in the hot loop).
+__device__ __forceinline__ void st2_out_if(bool pred, double* p, double2 v) {
+#if B200CG_STORE_HINT == 1
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.cs.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
+      "d"(v.x), "d"(v.y), "r"((int)pred)
+      : "memory");
+#else
+  if (pred) st2_out(p, v);
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
