@@ -6,12 +6,18 @@ Dirichlet system on an n x n grid through the C ABI (b200cg_solve), i.e. what Ma
   value : whole-job DOF-iterations/s with the right-hand side already resident in HBM and the solution left
           there; timed on the device (CUDA events of the library's solve stream), max over ranks.
   e2e   : the same solve with HOST buffers (pinned): H2D of b and D2H of x inside the timed region.
+  roofline / hbm_gbs_actual : REAL traffic (algorithmic bytes of the kernels that ran: 40 B per unknown-iteration for the
+          default single-sweep iteration) against the measured copy peak; model_80B: the same work expressed in SURVEY
+          8d's 80-byte store-Ap model (a work figure - it may exceed the physical bandwidth).
 N > 1 (torchrun, one process per GPU): row slabs of one larger grid, n_G = even(round(n * sqrt(G))), so the
 unknowns per GPU stay fixed (weak scaling, BASELINE.json configs[4]); halo rows and scalar reductions go over NVLink
 peer memory (NCCL as fallback) inside the library. --scaling strong shards the fixed --grid-n grid instead (configs[2]).
+Before the timed loop every N > 1 run checks 10 sharded solves against the CPU oracle (multi_gpu_parity).
 Workload at N = 1: the 16384^2 grid - the configuration BASELINE.json quotes its metric and target on ("a 16384^2 fp64
 Dirichlet CG solve at >= 70 % of B200 HBM bandwidth per GPU"; configs[2] and [4] at one GPU); it fits one GPU (17 GB).
-configs[1] (4096^2) and configs[3] (CSR, 8192^2) run with --grid-n 4096 / --op csr --grid-n 8192 and are parity-test cases.
+Extras of the default N = 1 line: two_sweep_extra (the two-sweep iteration on the same grid) and csr_extra
+(configs[3]: assembled CSR CG at 8192^2 beside the matrix-free iteration). configs[1] (4096^2) and configs[3] as lines
+of their own: --grid-n 4096 / --op csr --grid-n 8192.
 
 --impl reference times the reference's own CPU solver (unmodified sources compiled into oracle/_ref, else the
 C port in oracle/) on a bounded sample of the same workload, on rank 0 only.

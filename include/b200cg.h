@@ -188,7 +188,8 @@ int b200cg_partition(const b200cg_plan_desc* desc, int* y_lo, int* y_hi, int64_t
  * weights (n_weights entries, or NULL for the initial equal split) are the per-CTA shares feedback balancing
  * converges to. tiles holds `capacity` quadruples, cta_begin sms * ctas_per_sm + 1 ints. desc->reserved0 = 1 asks
  * for the single-sweep kernel's strips instead: 424 staged columns from storage column col0 = strip * 420 + 2, writing
- * x in [max(col0 - 2, xlo), min(col0 + 417, n - 1)]. */
+ * x in [max(col0 - 2, xlo), min(col0 + 417, n - 1)]; reserved0 = 2 for its wide geometry (slabs of >= 4 M unknowns: one
+ * 15-warp CTA per SM, 844 staged columns from col0 = strip * 840 + 2; call with ctas_per_sm = 1). */
 int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas_per_sm, const double* weights, int n_weights,
                       int* tiles, int64_t capacity, int64_t* n_tiles, int* cta_begin, int* grid);
 

@@ -136,10 +136,11 @@ def partition(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1):
 def work_split(m, n, domain=DOMAIN_LSHAPE, rank=0, world=1, sms=148, ctas_per_sm=2, weights=None, tile_rows=0,
                fused=False):
     """The sweep kernels' tile table for such a plan: (tiles[k, 4] = col0, ya, yb, xlo; cta_begin[grid + 1]).
-    fused: the single-sweep kernel's strip geometry (420 written columns from storage column strip * 420 + 2).
+    fused: the single-sweep kernel's strip geometry (1: 420 written columns from storage column strip * 420 + 2; 2: the wide
+    one of large slabs, 840 written columns).
     Pure host logic (b200cg_work_split) - works without a GPU."""
     desc = PlanDesc(n=int(n), m=int(m), a=0.0, b=1.0, c=0.0, d=1.0, domain=int(domain), device=0, rank=int(rank),
-                    world=int(world), tile_rows=int(tile_rows), reserved0=int(bool(fused)))
+                    world=int(world), tile_rows=int(tile_rows), reserved0=int(fused))
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     nw = 0 if w is None else int(w.size)
     count, grid = C.c_int64(), C.c_int()

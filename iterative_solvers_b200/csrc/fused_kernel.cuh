@@ -25,13 +25,14 @@
 
 namespace b200cg {
 
-constexpr int FUSED_CW = 7;                                  // consumer warps per CTA
-constexpr int FUSED_THREADS = (FUSED_CW + 1) * 32;           // + the producer warp
+constexpr int FUSED_CW = 7;                                  // consumer warps per CTA (default geometry)
 constexpr int FUSED_WARP_STEP = 60;                          // columns written per consumer warp (64 processed)
-constexpr int FUSED_COL_SHIFT = 2;                           // a strip's first staged storage column is strip * 420 + this
-constexpr int FUSED_STRIP_OUT = FUSED_WARP_STEP * FUSED_CW;  // 420 columns written per strip
-constexpr int FUSED_STRIP_COLS = FUSED_STRIP_OUT + 4;        // 424 staged columns: two halo columns per side
-constexpr int FUSED_ROW = FUSED_STRIP_COLS;                  // doubles between staged rows in shared memory (3392 B)
+constexpr int FUSED_COL_SHIFT = 2;                           // a strip's first staged storage column is strip * width + this
+__host__ __device__ constexpr int fused_strip_out(int cw) { return FUSED_WARP_STEP * cw; }   // columns written per strip: 420 (840)
+__host__ __device__ constexpr int fused_row(int cw) { return fused_strip_out(cw) + 4; }      // staged columns = doubles between staged rows
+constexpr int FUSED_STRIP_OUT = fused_strip_out(FUSED_CW);
+// CW = 14 (B200CG_FUSED_CW=14, experiment): one 15-warp CTA per SM on 840-column strips - half as many strip edges
+// (partial 128-byte lines, halo columns) per byte; profiles/r2_single_sweep.md
 
 template <int FLAGS>
 struct FusedCfg {
@@ -47,9 +48,9 @@ struct FusedCfg {
   static constexpr bool SHARD = (FLAGS & F_SHARD) != 0;
 };
 
-template <int FLAGS, int HS, int NST>
+template <int FLAGS, int HS, int NST, int CW>
 constexpr size_t fused_smem_bytes() {
-  return (size_t)NST * HS * FusedCfg<FLAGS>::NSTREAM * FUSED_ROW * 8 + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
+  return (size_t)NST * HS * FusedCfg<FLAGS>::NSTREAM * fused_row(CW) * 8 + (size_t)NST * (16 + sizeof(StageMeta)) + 128;
 }
 
 // The scalars of the next iteration from gamma' = r'.r' and delta' = r'.A r' (one thread, after the grid reduction).
@@ -78,11 +79,12 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
   st->pAp = gamma_new / alpha;
 }
 
-template <int FLAGS, int HS, int NST>
-__global__ void __launch_bounds__(FUSED_THREADS, 2) cg_fused_kernel(const TileArgs a) {
+template <int FLAGS, int HS, int NST, int CW = FUSED_CW>
+__global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fused_kernel(const TileArgs a) {
+  constexpr int FUSED_ROW = fused_row(CW), FUSED_STRIP_COLS = fused_row(CW);
   using Cfg = FusedCfg<FLAGS>;
   constexpr bool X2 = Cfg::X2, SHARD = Cfg::SHARD;
-  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW, CW = FUSED_CW;
+  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
   constexpr int STAGE_DOUBLES = HS * NSTREAM * FUSED_ROW;
   constexpr int OFF_P = 0, OFF_R = HS * FUSED_ROW, OFF_X = 2 * HS * FUSED_ROW;
 

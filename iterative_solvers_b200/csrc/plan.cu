@@ -465,6 +465,11 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->shape_dot = env_int("B200CG_SHAPE_DOT", P->shape_dot);
     P->shape_upd = env_int("B200CG_SHAPE_UPD", P->shape_upd);
     P->shape_nox = env_int("B200CG_SHAPE_NOX", P->shape_nox);
+    // single-sweep geometry: one 15-warp CTA per SM on 840-column strips for large slabs (half as many strip edges per
+    // byte: +1.8 % at 16384^2, +1.5 % at 4096^2), two 8-warp CTAs per SM on 420-column strips below ~4 M unknowns, where
+    // the number of CTAs matters more (1024^2: 49.7 against 44.3 GDOF-it/s) - profiles/r2_single_sweep.md
+    P->fused_cw = (!P->generic && P->g.hi - P->g.lo >= (4LL << 20)) ? 14 : FUSED_CW;
+    if (const char* env = getenv("B200CG_FUSED_CW")) P->fused_cw = atoi(env) == 14 ? 14 : FUSED_CW;
     P->x_deferral = env_int("B200CG_XDEFER", 1) != 0;
     P->balance_rounds = env_int("B200CG_BALANCE", 4);
     P->balance_rounds_fused = P->balance_rounds;
@@ -497,8 +502,8 @@ static int plan_create_impl(b200cg_plan_s* P) {
     P->tile_tab[0].ctas_per_sm = ctas_of(P->shape_dot);
     P->tile_tab[1].ctas_per_sm = ctas_of(P->shape_nox);
     P->tile_tab[2].ctas_per_sm = 2;  // every other flavour runs a 2-CTAs/SM shape
-    P->tile_tab[3].ctas_per_sm = 2;  // single-sweep iteration: its own strip geometry (fused_kernel.cuh)
-    P->tile_tab[3].strip_out = FUSED_STRIP_OUT;
+    P->tile_tab[3].ctas_per_sm = P->fused_cw == FUSED_CW ? 2 : 1;  // single-sweep iteration: its own strip geometry (fused_kernel.cuh)
+    P->tile_tab[3].strip_out = fused_strip_out(P->fused_cw);
     P->tile_tab[3].col_shift = FUSED_COL_SHIFT;
     if (P->shape_upd == 1) P->shape_upd = 0;
     for (auto& tt : P->tile_tab) RET(upload_tiles(P, &tt));
@@ -576,8 +581,8 @@ extern "C" int b200cg_work_split(const b200cg_plan_desc* desc, int sms, int ctas
   tmp.sms = sms;
   TileTable tt;
   tt.ctas_per_sm = ctas_per_sm;
-  if (desc->reserved0 == 1) {  // the single-sweep kernel's strip geometry
-    tt.strip_out = FUSED_STRIP_OUT;
+  if (desc->reserved0 == 1 || desc->reserved0 == 2) {  // the single-sweep kernel's strip geometries (2: the wide one)
+    tt.strip_out = fused_strip_out(desc->reserved0 == 2 ? 14 : FUSED_CW);
     tt.col_shift = FUSED_COL_SHIFT;
   }
   if (weights && n_weights > 0) tt.weight.assign(weights, weights + n_weights);

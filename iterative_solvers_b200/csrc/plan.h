@@ -85,6 +85,7 @@ struct b200cg_plan_s {
   TileTable tile_tab[4];  // sweep work lists per flavour
   int balance_rounds = 0;  // feedback-balancing steps still to do (the first graph launches of the plan)
   int balance_rounds_fused = 0;  // the same for the single-sweep flavour, counted from its own first launches
+  int fused_cw = FUSED_CW;                          // consumer warps of the single-sweep kernel: 7 (2 CTAs/SM) or 14 (1 CTA/SM, experiment)
   int shape_dot = 3, shape_upd = 2, shape_nox = 2;  // launch shapes of the hot flavours (launch_tile); measured best at 16384^2
   bool x_deferral = true;                           // REL_L2 without report: touch x every other iteration
   bool cluster_enabled = true;                      // small-grid path allowed (B200CG_CLUSTER=0 disables)

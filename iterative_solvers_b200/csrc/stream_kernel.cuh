@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, CTAS) cg_stream_kernel(const T
             xn.y = __dadd_rn(xo1, __dmul_rn(alpha, p1));
             rn.x = __dsub_rn(r0, __dmul_rn(alpha, ap0));
             rn.y = __dsub_rn(r1, __dmul_rn(alpha, ap1));
-            if (st_ok) {
+            if (FULL) {  // predicated stores: no divergent region in the unrolled path
+              if (!NOX) st2_out_if(st_ok, a.x + eoff, xn);
+              st2_out_if(st_ok, a.r_out + eoff, rn);
+              st2_out_if(st_ok, a.p_out + eoff, make_double2(p0, p1));
+            } else if (st_ok) {
               if (!NOX) st2_out(a.x + eoff, xn);
               st2_out(a.r_out + eoff, rn);
               st2_out(a.p_out + eoff, make_double2(p0, p1));

@@ -76,11 +76,11 @@ static int launch_tile(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
 }
 
 // The single-sweep iteration (fused_kernel.cuh): 8-warp CTAs, 2 CTAs/SM, 80-109 KB of copy destinations per CTA.
-template <int FLAGS, int HS, int NST>
+template <int FLAGS, int HS, int NST, int CW>
 static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
-  auto kernel = cg_fused_kernel<FLAGS, HS, NST>;
-  constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST>();
-  static_assert(smem + 1024 <= 114 * 1024, "two CTAs per SM");
+  auto kernel = cg_fused_kernel<FLAGS, HS, NST, CW>;
+  constexpr size_t smem = fused_smem_bytes<FLAGS, HS, NST, CW>();
+  static_assert(smem + 1024 <= (CW == FUSED_CW ? 114 : 227) * 1024, "two CTAs per SM (one for the wide geometry)");
   static thread_local bool configured[64] = {};
   const int dev = P->desc.device & 63;
   if (!configured[dev]) {
@@ -93,7 +93,7 @@ static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
   a.cta_begin = tt.d_cta_begin;
   a.cta_clock = P->d_clock[3];
   P->clock_ctas[3] = tt.grid;
-  kernel<<<tt.grid, FUSED_THREADS, smem, s>>>(a);
+  kernel<<<tt.grid, (CW + 1) * 32, smem, s>>>(a);
   CU(cudaGetLastError());
   return B200CG_OK;
 }
@@ -102,8 +102,12 @@ static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
 // 1.5 %, these two on top (profiles/r2_single_sweep.md) - the ring is deep enough, so the alternatives are gone.
 template <int FLAGS>
 static int launch_fused_flags(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2>(P, a, s);
-  else return launch_fused_cfg<FLAGS, 4, 3>(P, a, s);
+  if (P->fused_cw == 14) {  // experiment: one wide CTA per SM
+    if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2, 14>(P, a, s);
+    else return launch_fused_cfg<FLAGS, 4, 4, 14>(P, a, s);
+  }
+  if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2, FUSED_CW>(P, a, s);
+  else return launch_fused_cfg<FLAGS, 4, 3, FUSED_CW>(P, a, s);
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {

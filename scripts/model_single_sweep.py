@@ -128,7 +128,7 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
             k0b = row_ok & (x0 + 1 >= xlo) & (x0 + 1 <= G.n - 1)
             if stored:
                 def stage(src):
-                    buf = np.full(STRIP_LOAD, np.nan)  # what the bulk copy does not write stays stale
+                    buf = np.full(strip_cols, np.nan)  # what the bulk copy does not write stays stale
                     buf[:row_doubles] = src[ri, col0:col0 + row_doubles]
                     return buf
                 sp, sr = stage(p_in), stage(r_in)
@@ -186,9 +186,11 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
 
 
 def run(n, m, lshape, iters, tile_rows=0, sms=4, warps=WARPS):
+    """warps: 7 (420-column strips, two CTAs per SM) or 14 (the wide geometry of large slabs: 840-column strips)."""
     G = Grid(n, m, lshape)
     domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
-    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2, tile_rows=tile_rows, fused=True)
+    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2 if warps == 7 else 1, tile_rows=tile_rows,
+                               fused=2 if warps == 14 else 1)
     rng = np.random.default_rng(n * 1000 + m)
     b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
 
@@ -299,6 +301,10 @@ if __name__ == "__main__":
                                     (900, 30, True, 3, 0), (430, 26, False, 3, 4), (845, 64, True, 3, 0)]:
         worst, dx, dr, nt = run(n, m, lshape, iters, tr)
         print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
+        assert worst < 1e-12 and dx < 1e-10 and dr < 1e-10
+    for n, m, lshape, iters, tr in [(64, 64, True, 4, 0), (900, 30, True, 3, 0), (1700, 26, False, 3, 4), (1690, 64, True, 3, 0)]:
+        worst, dx, dr, nt = run(n, m, lshape, iters, tr, warps=14)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} wide geometry: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
         assert worst < 1e-12 and dx < 1e-10 and dr < 1e-10
     for n, m, lshape, iters, world, tr in [(64, 64, True, 6, 2, 0), (64, 64, True, 5, 3, 0), (130, 90, True, 5, 4, 0),
                                            (77, 60, False, 5, 3, 5), (1000, 40, True, 4, 2, 0), (96, 96, True, 7, 8, 0)]:

@@ -167,6 +167,191 @@ __global__ void __launch_bounds__((CONS_WARPS + 2) * 32, 2) ring_kernel(Args a) 
   }
 }
 
+// The product's access pattern: the vectors are 2-D [R][pitch]; a CTA marches down a strip of COLS columns, so its
+// consecutive row copies are `pitch` doubles apart in memory (131 KB at 16384^2) instead of adjacent.
+template <int NIN, int NOUT, int HS, int NST, int COLS, int SPLIT = 0>
+__global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 2) strip_kernel(Args a, int pitch, int R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE = HS * NIN * COLS;
+  double* data = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE * 8);
+  uint64_t* empty = full + NST;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], CONS_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int strips = pitch / COLS;
+  const long long total = (long long)strips * R;  // (strip, row) pairs, strip-major
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long t0 = (long long)blockIdx.x * per, t1 = t0 + per < total ? t0 + per : total;
+  if (warp == CONS_WARPS) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = t0; t < t1;) {
+        const int strip = (int)(t / R), row = (int)(t % R);
+        const int nr = (int)min((long long)HS, min((long long)(R - row), t1 - t));
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(nr * NIN * COLS * 8));
+        double* sd = data + (size_t)stage * STAGE;
+        for (int j = 0; j < nr; ++j)
+          for (int k = 0; k < NIN; ++k) {
+            double* dst = sd + (k * HS + j) * COLS;
+            const double* src = a.in[k] + (size_t)(row + j) * pitch + (size_t)strip * COLS;
+            if (SPLIT) {  // head up to the next 128-byte line, aligned middle, tail
+              const int head = (int)((16 - (((size_t)strip * COLS) & 15)) & 15);
+              const int mid = (COLS - head) & ~15, tail = COLS - head - mid;
+              if (head) bulk_g2s(dst, src, head * 8, &full[stage]);
+              bulk_g2s(dst + head, src + head, mid * 8, &full[stage]);
+              if (tail) bulk_g2s(dst + head + mid, src + head + mid, tail * 8, &full[stage]);
+            } else {
+              bulk_g2s(dst, src, COLS * 8, &full[stage]);
+            }
+          }
+        t += nr;
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t0; t < t1;) {
+      const int strip = (int)(t / R), row = (int)(t % R);
+      const int nr = (int)min((long long)HS, min((long long)(R - row), t1 - t));
+      mbar_wait(&full[stage], phase);
+      const double* sd = data + (size_t)stage * STAGE;
+      for (int c = 2 * tid; c + 1 < COLS; c += 2 * CONS_WARPS * 32) {
+        for (int j = 0; j < nr; ++j) {
+          double2 v[NIN];
+#pragma unroll
+          for (int k = 0; k < NIN; ++k) v[k] = *reinterpret_cast<const double2*>(sd + (k * HS + j) * COLS + c);
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k) {
+            double2 o;
+            o.x = v[0].x + 1.0000001 * v[k < NIN ? k : 0].x;
+            o.y = v[0].y + 1.0000001 * v[k < NIN ? k : 0].y;
+            __stcs(reinterpret_cast<double2*>(a.out[k] + (size_t)(row + j) * pitch + (size_t)strip * COLS + c), o);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      t += nr;
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+  }
+}
+
+// The product's geometry: a strip OWNS `OWN` columns (stores exactly those) and stages LOAD >= OWN columns starting
+// SHIFT columns to the left (halo columns); throughput is counted on the owned bytes only.
+template <int NIN, int NOUT, int HS, int NST, int OWN, int LOAD, int SHIFT>
+__global__ void __launch_bounds__((CONS_WARPS + 1) * 32, 2) halo_kernel(Args a, int pitch, int R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE = HS * NIN * LOAD;
+  double* data = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE * 8);
+  uint64_t* empty = full + NST;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], CONS_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int strips = (pitch - 64) / OWN;  // (the first strip starts 32 columns in, so halos stay inside the row)
+  const long long total = (long long)strips * R;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long t0 = (long long)blockIdx.x * per, t1 = t0 + per < total ? t0 + per : total;
+  if (warp == CONS_WARPS) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = t0; t < t1;) {
+        const int strip = (int)(t / R), row = (int)(t % R);
+        const int nr = (int)min((long long)HS, min((long long)(R - row), t1 - t));
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(nr * NIN * LOAD * 8));
+        double* sd = data + (size_t)stage * STAGE;
+        for (int j = 0; j < nr; ++j)
+          for (int k = 0; k < NIN; ++k)
+            bulk_g2s(sd + (k * HS + j) * LOAD, a.in[k] + (size_t)(row + j) * pitch + 32 + (size_t)strip * OWN - SHIFT, LOAD * 8,
+                     &full[stage]);
+        t += nr;
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t0; t < t1;) {
+      const int strip = (int)(t / R), row = (int)(t % R);
+      const int nr = (int)min((long long)HS, min((long long)(R - row), t1 - t));
+      mbar_wait(&full[stage], phase);
+      const double* sd = data + (size_t)stage * STAGE;
+      for (int c = 2 * tid; c + 1 < OWN; c += 2 * CONS_WARPS * 32) {
+        for (int j = 0; j < nr; ++j) {
+          double2 v[NIN];
+#pragma unroll
+          for (int k = 0; k < NIN; ++k) v[k] = *reinterpret_cast<const double2*>(sd + (k * HS + j) * LOAD + SHIFT + c);
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k) {
+            double2 o;
+            o.x = v[0].x + 1.0000001 * v[k < NIN ? k : 0].x;
+            o.y = v[0].y + 1.0000001 * v[k < NIN ? k : 0].y;
+            __stcs(reinterpret_cast<double2*>(a.out[k] + (size_t)(row + j) * pitch + 32 + (size_t)strip * OWN + c), o);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      t += nr;
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+  }
+}
+template <int NIN, int NOUT, int HS, int NST, int OWN, int LOAD, int SHIFT>
+float run_halo(const Args& a, int sms, int reps, int pitch, int R) {
+  auto k = halo_kernel<NIN, NOUT, HS, NST, OWN, LOAD, SHIFT>;
+  const size_t smem = (size_t)NST * HS * NIN * LOAD * 8 + NST * 16 + 128;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) k<<<2 * sms, (CONS_WARPS + 1) * 32, smem>>>(a, pitch, R);
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < reps; ++i) k<<<2 * sms, (CONS_WARPS + 1) * 32, smem>>>(a, pitch, R);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms / reps;
+}
+
+template <int NIN, int NOUT, int HS, int NST, int COLS, int SPLIT = 0>
+float run_strip(const Args& a, int sms, int reps, int pitch, int R) {
+  auto k = strip_kernel<NIN, NOUT, HS, NST, COLS, SPLIT>;
+  const size_t smem = (size_t)NST * HS * NIN * COLS * 8 + NST * 16 + 128;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) k<<<2 * sms, (CONS_WARPS + 1) * 32, smem>>>(a, pitch, R);
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < reps; ++i) k<<<2 * sms, (CONS_WARPS + 1) * 32, smem>>>(a, pitch, R);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms / reps;
+}
+
 template <int NIN, int NOUT, int HS, int NST, int MODE>
 float run_ring(const Args& a, int sms, int reps) {
   auto k = ring_kernel<NIN, NOUT, HS, NST, MODE>;
@@ -246,5 +431,38 @@ int main(int argc, char** argv) {
   report("bulk-load ring HS4 + bulk store (in place)", 3, 3, run_ring<3, 3, 4, 2, 2>(a, sms, reps));
   report("bulk-load ring HS2 + bulk store (in place)", 2, 2, run_ring<2, 2, 2, 6, 2>(a, sms, reps));
   report("bulk-load ring HS2 + bulk store (in place)", 3, 3, run_ring<3, 3, 2, 4, 2>(a, sms, reps));
+  {  // strips of a pitched 2-D array (16384 rows x 16384 columns: 2 GiB per vector)
+    const int pitch = 16384, R = (int)(n / pitch);
+    auto rep2 = [&](const char* name, int nin, int nout, int cols, float ms) {
+      const double bytes = (double)(nin + nout) * (double)(pitch / cols) * cols * R * 8;
+      printf("%-44s %d in %d out  %8.3f ms  %8.1f GB/s\n", name, nin, nout, ms, bytes / ms / 1e6);
+      fflush(stdout);
+    };
+    rep2("strip march, 512-column strips, HS4", 2, 2, 512, run_strip<2, 2, 4, 3, 512>(a, sms, reps, pitch, R));
+    rep2("strip march, 512-column strips, HS4", 3, 3, 512, run_strip<3, 3, 4, 2, 512>(a, sms, reps, pitch, R));
+    rep2("strip march, 424-column strips, HS4", 2, 2, 424, run_strip<2, 2, 4, 3, 424>(a, sms, reps, pitch, R));
+    rep2("strip march, 424-column strips, HS4", 3, 3, 424, run_strip<3, 3, 4, 2, 424>(a, sms, reps, pitch, R));
+    rep2("strip march, 424 columns, split at 128-B lines", 2, 2, 424, run_strip<2, 2, 4, 3, 424, 1>(a, sms, reps, pitch, R));
+    rep2("strip march, 424 columns, split at 128-B lines", 3, 3, 424, run_strip<3, 3, 4, 2, 424, 1>(a, sms, reps, pitch, R));
+    rep2("strip march, 416-column strips, HS4", 2, 2, 416, run_strip<2, 2, 4, 3, 416>(a, sms, reps, pitch, R));
+    rep2("strip march, 432-column strips, HS4", 2, 2, 432, run_strip<2, 2, 4, 3, 432>(a, sms, reps, pitch, R));
+    rep2("strip march, 448-column strips, HS4", 2, 2, 448, run_strip<2, 2, 4, 3, 448>(a, sms, reps, pitch, R));
+    rep2("strip march, 448-column strips, HS4", 3, 3, 448, run_strip<3, 3, 4, 2, 448>(a, sms, reps, pitch, R));
+    auto rep3 = [&](const char* name, int nin, int nout, int own, float ms) {
+      const double bytes = (double)(nin + nout) * (double)((pitch - 64) / own) * own * R * 8;
+      printf("%-52s %d in %d out  %8.3f ms  %8.1f GB/s of OWNED bytes\n", name, nin, nout, ms, bytes / ms / 1e6);
+      fflush(stdout);
+    };
+    rep3("own 420 (32-B aligned), load 424 @-2 [product]", 2, 2, 420, run_halo<2, 2, 4, 3, 420, 424, 2>(a, sms, reps, pitch, R));
+    rep3("own 420 (32-B aligned), load 424 @-2 [product]", 3, 3, 420, run_halo<3, 3, 4, 2, 420, 424, 2>(a, sms, reps, pitch, R));
+    rep3("own 416 (line aligned), load 420 @-2", 2, 2, 416, run_halo<2, 2, 4, 3, 416, 420, 2>(a, sms, reps, pitch, R));
+    rep3("own 416 (line aligned), load 420 @-2", 3, 3, 416, run_halo<3, 3, 4, 2, 416, 420, 2>(a, sms, reps, pitch, R));
+    rep3("own 416 (line aligned), load 448 @-16 (aligned)", 2, 2, 416, run_halo<2, 2, 4, 3, 416, 448, 16>(a, sms, reps, pitch, R));
+    rep3("own 416 (line aligned), load 448 @-16 (aligned)", 3, 3, 416, run_halo<3, 3, 4, 2, 416, 448, 16>(a, sms, reps, pitch, R));
+    rep3("own 832 (line aligned), load 864 @-16 (aligned)", 2, 2, 832, run_halo<2, 2, 2, 3, 832, 864, 16>(a, sms, reps, pitch, R));
+    rep3("own 480 (line aligned), load 484 @-2", 2, 2, 480, run_halo<2, 2, 4, 3, 480, 484, 2>(a, sms, reps, pitch, R));
+    rep2("strip march, 256-column strips, HS4", 2, 2, 256, run_strip<2, 2, 4, 6, 256>(a, sms, reps, pitch, R));
+    rep2("strip march, 1024-column strips, HS2", 2, 2, 1024, run_strip<2, 2, 2, 3, 1024>(a, sms, reps, pitch, R));
+  }
   return 0;
 }

@@ -17,17 +17,19 @@ from oracle.oracle import Oracle  # noqa: E402
 
 FULL_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
               (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
-              (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s")]
+              (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s"), (256, 0, 1e-8, "mf-w"),
+              (1100, 0, 1e-6, "mf-w")]
 # bench.py runs these in-process before its timed loop at N > 1 (the oracle solves take ~20 s of rank 0's host time)
 BENCH_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (500, 0, 1e-5, "mf"), (333, 1, 1e-8, "mf"),
                (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
-               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s")]
+               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (256, 0, 1e-8, "mf-w"), (500, 0, 1e-5, "mf-w")]
 
 
 def run_cases(rank, world, local, cases, log=print):
     """Every rank calls this inside an initialised NCCL process group. Kinds: "mf" = the default iteration (single sweep:
     two halo rows per side over peer memory, one publish-and-wait per iteration), "mf-2s" = the two-sweep iteration,
-    "mf-hs2" = two sweeps with 2-row stages (the launch shapes are read when the plan is created), "msg" / "msg0" = the
+    "mf-hs2" = two sweeps with 2-row stages (the launch shapes are read when the plan is created), "mf-w" = the single
+    sweep in the wide geometry of large slabs (840-column strips, one CTA per SM) forced onto a small grid, "msg" / "msg0" = the
     max-norm rules with / without a true solution, "cb" = the per-iteration report callback.
     Returns {"cases", "ok", "max_rel", "iterations_equal", "failed"} (meaningful on rank 0)."""
 
@@ -45,9 +47,11 @@ def run_cases(rank, world, local, cases, log=print):
         b, u = o.rhs(), o.true_solution()
         if kind == "mf-hs2":
             os.environ.update(hs2)
+        if kind == "mf-w":
+            os.environ["B200CG_FUSED_CW"] = "14"
         plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local, rank=rank, world=world,
                          comm_id=fresh_comm_id())
-        for k in list(hs2):
+        for k in list(hs2) + ["B200CG_FUSED_CW"]:
             os.environ.pop(k, None)
         lo, hi = plan.lo, plan.hi
         got_cb = []
@@ -61,8 +65,8 @@ def run_cases(rank, world, local, cases, log=print):
 
         # the GPU solve first, on all ranks together; rank 0 computes the reference afterwards while the others wait in
         # the gather below (inside a solve a rank waits at most 20 s for its peers)
-        if kind in ("mf", "mf-hs2", "mf-2s"):
-            two = kind != "mf"
+        if kind in ("mf", "mf-hs2", "mf-2s", "mf-w"):
+            two = kind in ("mf-hs2", "mf-2s")
             x, info = plan.solve(b=b[lo:hi], eps_rel=eps, max_it=20000, single_sweep=2 if two else 0)
             if info["single_sweep"] != (0 if two else 1):
                 failures.append((n, domain, kind, "wrong iteration scheme"))

@@ -119,3 +119,22 @@ def test_large_grid_property(capi):
         assert isf["iterations"] == idf["iterations"] == 60
         assert relmax(xs, xd) < 1e-11
         assert abs(isf["r_l2"] - idf["r_l2"]) <= 1e-10 * idf["r_l2"]
+
+
+@pytest.mark.parametrize("n,domain,tile_rows,eps", [(64, 0, 0, 1e-8), (64, 0, 3, 1e-8), (900, 0, 0, 1e-6), (1030, 0, 7, 1e-5),
+                                                     (333, 1, 0, 1e-8), (1709, 1, 5, 1e-4)])
+def test_wide_geometry_forced_on_small_grids(capi, oracle_mod, n, domain, tile_rows, eps):
+    """Slabs of >= 4 M unknowns run the single sweep as one 15-warp CTA per SM on 840-column strips (test_large_grid_property,
+    the 4096^2 and 16384^2 tests); B200CG_FUSED_CW=14 forces that geometry onto grids the oracle solves in seconds."""
+    import os
+
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0, domain)
+    ref = o.mf_solve(eps=eps, max_it=20000)
+    os.environ["B200CG_FUSED_CW"] = "14"
+    try:
+        with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, tile_rows=tile_rows) as p:  # the knob is read here
+            x, info = fused_solve(p, b=o.rhs(), eps_rel=eps, max_it=20000)
+    finally:
+        os.environ.pop("B200CG_FUSED_CW", None)
+    assert abs(info["iterations"] - ref["iterations"]) <= 1
+    assert relmax(x, ref["x"]) < REL

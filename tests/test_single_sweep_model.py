@@ -42,3 +42,11 @@ def test_strips_with_stale_columns_and_full_stages(model, n, m, lshape, iters, t
     for FULL stages, strips crossing the re-entrant edge of the L."""
     worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows)
     assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
+
+
+@pytest.mark.parametrize("n,m,lshape,iters,tile_rows", [(64, 64, True, 4, 0), (900, 30, True, 3, 0), (1700, 26, False, 3, 4),
+                                                        (1690, 64, True, 3, 0)])
+def test_wide_geometry_model(model, n, m, lshape, iters, tile_rows):
+    """Slabs of >= 4 M unknowns run one 15-warp CTA per SM on 840-column strips (14 consumer warps): same data flow."""
+    worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows, warps=14)
+    assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12

@@ -48,7 +48,7 @@ def check_split(n, m, domain, world, sms, ctas, weights=None, tile_rows=0, fused
             assert np.all(lower | (tiles[:, 1] > m // 2))
             assert np.all(tiles[lower & (tiles[:, 1] <= m // 2), 3] == n // 2 + 1)
             assert np.all(tiles[tiles[:, 1] > m // 2, 3] == 1)
-        cov = coverage(n, m, tiles, FUSED_STRIP_OUT, FUSED_SHIFT) if fused else coverage(n, m, tiles)
+        cov = coverage(n, m, tiles, FUSED_STRIP_OUT * int(fused), FUSED_SHIFT) if fused else coverage(n, m, tiles)
         assert cov.sum() == hi - lo
         total += cov
     assert np.array_equal(total, unknown_mask(n, m, domain))
@@ -116,3 +116,6 @@ def test_single_sweep_strip_geometry(n):
     check_split(n, n + 3, capi.DOMAIN_RECT, 1, 148, 2, fused=True, tile_rows=3)
     check_split(n + 1, n, capi.DOMAIN_LSHAPE_ANY, 1, 4, 2, fused=True)
     check_split(n, n + 1, capi.DOMAIN_RECT, 2, 16, 2, fused=True) if n >= 8 else None
+    # the wide geometry of large slabs (desc.reserved0 = 2): 840 written columns, one CTA per SM
+    check_split(n, n, capi.DOMAIN_LSHAPE, 1, 148, 1, fused=2)
+    check_split(2 * n + 2, n + 3, capi.DOMAIN_RECT, 3, 16, 1, fused=2) if n >= 8 else None
