@@ -133,6 +133,7 @@ static int vcycle(b200cg_plan_s* P, int l, int64_t* launches) {
 }
 
 int b200cg::mg_levels(const b200cg_plan_s* P) { return P->mg ? (int)P->mg->levels.size() : 0; }
+int b200cg::mg_prepare(b200cg_plan_s* P) { return mg_setup(P); }
 
 // The PCG loop. On entry the init kernel has run (r[0] = b, x = 0, p[0] = 0, ||r0|| in the device state and its verdict for
 // max_it = 0 / b = 0); on exit the device state mirror holds the result like after the plain loop.

@@ -640,6 +640,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   c.use_cluster = cl_ctas > 0 && !mg;
   if (mg) {
     // opt-in: CG preconditioned by a multigrid V-cycle (mg.cu) - its own loop, same init kernel and stop rule
+    RET(mg_prepare(P));
     RET(launch_init(c));
     CU(cudaEventRecord(P->ev[5], s));
     RET(mg_pcg_solve(P, stop_flag, &info->kernel_launches, &c.interrupted));

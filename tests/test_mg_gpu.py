@@ -51,6 +51,7 @@ def test_same_solution_as_plain_cg_in_a_fraction_of_the_iterations(capi):
     with capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0) as p:
         p.build_rhs()
         u = p.true_solution()
+        p.solve(rhs_on_device=True, eps_rel=1e-9, max_it=1, preconditioner=capi.PRECOND_MULTIGRID)  # builds the hierarchy
         xm, im = p.solve(rhs_on_device=True, eps_rel=1e-9, max_it=200, preconditioner=capi.PRECOND_MULTIGRID)
         assert im["converged"] and im["iterations"] <= 10
         res, _ = p.postprocess(want_error=False)
