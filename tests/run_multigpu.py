@@ -18,18 +18,20 @@ from oracle.oracle import Oracle  # noqa: E402
 FULL_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
               (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s"), (256, 0, 1e-8, "mf-w"),
-              (1100, 0, 1e-6, "mf-w")]
+              (1100, 0, 1e-6, "mf-w"), (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s")]
 # bench.py runs these in-process before its timed loop at N > 1 (the oracle solves take ~20 s of rank 0's host time)
 BENCH_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (500, 0, 1e-5, "mf"), (333, 1, 1e-8, "mf"),
                (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
-               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (256, 0, 1e-8, "mf-w"), (500, 0, 1e-5, "mf-w")]
+               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (256, 0, 1e-8, "mf-w"), (500, 0, 1e-5, "mf-w"),
+               (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s")]
 
 
 def run_cases(rank, world, local, cases, log=print):
     """Every rank calls this inside an initialised NCCL process group. Kinds: "mf" = the default iteration (single sweep:
     two halo rows per side over peer memory, one publish-and-wait per iteration), "mf-2s" = the two-sweep iteration,
     "mf-hs2" = two sweeps with 2-row stages (the launch shapes are read when the plan is created), "mf-w" = the single
-    sweep in the wide geometry of large slabs (840-column strips, one CTA per SM) forced onto a small grid, "msg" / "msg0" = the
+    sweep in the wide geometry of large slabs (840-column strips, one CTA per SM) forced onto a small grid, "stop" /
+    "stop-2s" = an interrupt raised on rank 0 ONLY must end the solve on every rank at the same iteration, "msg" / "msg0" = the
     max-norm rules with / without a true solution, "cb" = the per-iteration report callback.
     Returns {"cases", "ok", "max_rel", "iterations_equal", "failed"} (meaningful on rank 0)."""
 
@@ -63,6 +65,24 @@ def run_cases(rank, world, local, cases, log=print):
                 refs[key] = fn()
             return refs[key]
 
+        if kind in ("stop", "stop-2s"):
+            # requestStop on one rank: the request travels with the per-iteration reductions (kernels poll the mapped flag
+            # every 16th iteration), so all ranks report INTERRUPTED after the same 16 iterations
+            import ctypes
+
+            flag = ctypes.c_int(1 if rank == 0 else 0)
+            x, info = plan.solve(b=b[lo:hi], eps_rel=1e-30, max_it=100000, iters_per_graph=100, stop_flag=flag,
+                                 single_sweep=2 if kind == "stop-2s" else 0)
+            plan.close()
+            seen = [None] * world
+            dist.all_gather_object(seen, (info["iterations"], info["stop_reason"], info["converged"]))
+            ok = all(s == (16, "INTERRUPTED", False) for s in seen)
+            if rank == 0:
+                log(f"[multigpu] n={n} domain={domain} {kind}: per-rank (iterations, stop reason, converged) = {seen} -> "
+                    f"{'ok' if ok else 'FAIL'}")
+                if not ok:
+                    failures.append((n, domain, kind))
+            continue
         # the GPU solve first, on all ranks together; rank 0 computes the reference afterwards while the others wait in
         # the gather below (inside a solve a rank waits at most 20 s for its peers)
         if kind in ("mf", "mf-hs2", "mf-2s", "mf-w"):
