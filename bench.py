@@ -378,32 +378,70 @@ def run_b200(args):
     value = total_dofit / (dev_ms * 1e-3) / 1e9
     launches_all = int(sum_over_ranks(float(launches)))
 
-    # ---- e2e: host buffers through the C ABI
+    # ---- e2e: host buffers through the C ABI. Headline: the steps as ONE queue of right-hand sides (b200cg_solve_batch):
+    # every step's b goes H2D from pinned memory and every step's x comes back D2H and is read on the host, all inside
+    # the timed region - the copies of neighbouring steps run on copy streams under the current step's iterations.
+    # Beside it: the same steps as separate b200cg_solve calls (copies serialised with the solve), on fewer steps.
     e2e = None
     if not args.no_e2e:
         hb = capi.PinnedArray(n_local)
-        hx = capi.PinnedArray(n_local)
+        hx = [capi.PinnedArray(n_local), capi.PinnedArray(n_local)]
         hb.array[:] = plan.get_rhs()
-        for _ in range(max(1, min(args.warmup, 2))):
-            plan.solve(b=hb.array, x_out=hx.array, **solve_kw)
-        barrier()
-        t0 = time.perf_counter()
-        e_its, e_dev = 0, 0.0
-        for _ in range(args.steps):
-            _, info = plan.solve(b=hb.array, x_out=hx.array, **solve_kw)
-            e_its += info["iterations"]
-            e_dev += info["device_ms"]
-            checksum = float(hx.array[0] + hx.array[-1])  # the D2H result is read on the host every step
-        barrier()
-        e_wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        e2e = {"value": float(plan.N) * e_its / (e_wall * 1e-3) / 1e9, "unit": UNIT,
+        batch_kw = dict(rule=capi.RULE_REL_L2, eps_rel=0.0, max_it=args.iters, iters_per_graph=args.iters_per_graph,
+                        single_sweep=args.single_sweep)
+        checks = []
+
+        def serial_leg(steps):
+            for _ in range(max(1, min(args.warmup, 2))):
+                plan.solve(b=hb.array, x_out=hx[0].array, **solve_kw)
+            barrier()
+            t0 = time.perf_counter()
+            its, dev = 0, 0.0
+            for _ in range(steps):
+                _, info = plan.solve(b=hb.array, x_out=hx[0].array, **solve_kw)
+                its += info["iterations"]
+                dev += info["device_ms"]
+                checks.append(float(hx[0].array[0] + hx[0].array[-1]))  # the D2H result is read on the host every step
+            barrier()
+            wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            return {"value": float(plan.N) * its / (wall * 1e-3) / 1e9, "unit": UNIT, "steps": steps,
+                    "ms_per_step": wall / max(steps, 1), "device_ms_per_step": max_over_ranks(dev) / max(steps, 1)}
+
+        def batch_leg(steps):
+            outs = [hx[i & 1].array for i in range(steps)]
+            plan.solve_batch([hb.array] * 2, [hx[0].array, hx[1].array], **batch_kw)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            infos = plan.solve_batch([hb.array] * steps, outs, **batch_kw,
+                                     done=lambda i, info: checks.append(float(outs[i][0] + outs[i][-1])))
+            barrier()
+            wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            its = sum(info["iterations"] for info in infos)
+            return {"value": float(plan.N) * its / (wall * 1e-3) / 1e9, "unit": UNIT, "steps": steps,
+                    "ms_per_step": wall / max(steps, 1)}
+
+        serial = serial_leg(args.steps if args.op == "csr" else max(1, min(args.steps, 3)))
+        batch, batch_err = None, None
+        if args.op == "mf":
+            try:
+                batch = batch_leg(args.steps)
+            except Exception as exc:  # the queue is an addition: its failure must not cost the line
+                batch_err = repr(exc)
+        head = batch or serial
+        e2e = {"value": head["value"], "unit": UNIT,
                "h2d_bytes_per_step": int(sum_over_ranks(float(n_local * 8))),
                "d2h_bytes_per_step": int(sum_over_ranks(float(n_local * 8))),
-               "ms_per_step": e_wall / max(args.steps, 1), "device_ms_per_step": max_over_ranks(e_dev) / max(args.steps, 1),
+               "ms_per_step": head["ms_per_step"],
+               "mode": ("b200cg_solve_batch: the steps as one queue of right-hand sides, each step's H2D of b and D2H of x "
+                        "(pinned host buffers) on copy streams under the neighbouring steps' iterations"
+                        if batch else "b200cg_solve per step: H2D of b, solve, D2H of x one after the other"),
+               "one_call_per_step": serial, "batch_error": batch_err,
                "timing": "host wall clock around the C-ABI calls, barrier + device synchronize on both sides",
-               "checksum": checksum, "host_numa_binding_rank0": numa}
+               "checksum": checks[-1] if checks else None, "results_read_on_host": len(checks),
+               "host_numa_binding_rank0": numa}
         hb.free()
-        hx.free()
+        for h in hx:
+            h.free()
 
     if rank != 0:
         plan.close()

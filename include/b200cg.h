@@ -228,6 +228,22 @@ int b200cg_csr_apply(b200cg_plan_t plan, const double* x_host, double* y_host);
 int b200cg_solve(b200cg_plan_t plan, const b200cg_params* params, const double* b_host, const double* u_host,
                  double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user, const volatile int* stop_flag);
 
+/* A queue of right-hand sides through one plan (time steps, parameter sweeps; bench.py's end-to-end leg): `count`
+ * back-to-back b200cg_solve calls on the matrix-free operator (MatrixFreeSolver::solve, matrix_free_system.cpp:383-482,
+ * once per rhs) whose host copies overlap the iterations - the H2D copy of b_hosts[i+1] and the D2H copy of x_hosts[i-1]
+ * run on two copy streams (second staging buffer) while solve i iterates, so only the first upload and the last download
+ * are exposed. Same arithmetic, same results as `count` separate calls. No true solution, no iteration callback;
+ * params->rhs_on_device and keep_x_on_device must be 0; pinned host buffers (b200cg_alloc_pinned) are what makes the
+ * copies asynchronous. x_hosts[i] may be read (and b_hosts[i] / x_hosts[i] reused) once done(user, i, &infos[i]) has
+ * been called - on the calling thread, in order, at the latest before the function returns. A stop request ends the
+ * queue with the solve it interrupts; the infos of the solves never started carry B200CG_STOP_INTERRUPTED and
+ * iterations = 0. Inside a batch info.h2d_ms / d2h_ms / device_ms cover the scatter / gather kernels only. On a sharded
+ * plan every rank calls it with the same count and params. */
+typedef void (*b200cg_batch_cb)(void* user, int index, const b200cg_info* info);
+int b200cg_solve_batch(b200cg_plan_t plan, const b200cg_params* params, int count, const double* const* b_hosts,
+                       double* const* x_hosts, b200cg_info* infos, b200cg_batch_cb done, void* user,
+                       const volatile int* stop_flag);
+
 /* ------------------------------------------------------------------ post-processing on the last solution
  * residual = A x - b and error = x - u: DirichletSolver::computeResidual / computeError
  * (dirichlet_solver.cpp:147-180). Either output may be NULL. op selects the stencil or the CSR matrix. */

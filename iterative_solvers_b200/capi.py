@@ -23,7 +23,7 @@ EXPORTS = [
     "b200cg_partition", "b200cg_work_split",
     "b200cg_build_rhs", "b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_coords",
     "b200cg_apply", "b200cg_set_csr", "b200cg_assemble_csr", "b200cg_get_csr", "b200cg_csr_apply",
-    "b200cg_solve", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times", "b200cg_peer_trace",
+    "b200cg_solve", "b200cg_solve_batch", "b200cg_postprocess", "b200cg_get_solution", "b200cg_cta_times", "b200cg_peer_trace",
 ]
 
 
@@ -67,6 +67,7 @@ class SolveInfo(C.Structure):
 
 
 ITER_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double)
+BATCH_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(SolveInfo))
 
 _lib = None
 
@@ -83,6 +84,8 @@ def lib():
         L.b200cg_plan_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(PlanDesc)]
         L.b200cg_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(SolveInfo), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200cg_solve_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p), C.POINTER(SolveInfo), C.c_void_p, C.c_void_p, C.c_void_p]
         for name in ("b200cg_plan_destroy", "b200cg_build_rhs"):
             getattr(L, name).argtypes = [C.c_void_p]
         for name in ("b200cg_set_rhs", "b200cg_get_rhs", "b200cg_get_true_solution", "b200cg_get_solution"):
@@ -303,6 +306,28 @@ class Plan:
         check(self.L.b200cg_solve(self.h, C.byref(prm), _ptr(b), _ptr(u), _ptr(x_out), C.byref(info),
                                   C.cast(cb, C.c_void_p) if cb else None, None, flag_ptr))
         return x_out, info.as_dict()
+
+    def solve_batch(self, bs, xs, done=None, rule=RULE_REL_L2, eps_rel=1e-6, max_it=10000, iters_per_graph=0,
+                    stop_flag=None, small_grid_path=0, single_sweep=0, preconditioner=0, op=OP_MATRIX_FREE):
+        """b200cg_solve_batch: one matrix-free solve per right-hand side of `bs` into the arrays of `xs` (numpy arrays or
+        PinnedArray.array views; the lists may repeat buffers), copies overlapped with the iterations. done(i, info dict)
+        fires once xs[i] is complete. Returns the list of info dicts."""
+        count = len(bs)
+        assert len(xs) == count
+        prm = Params(op=op, rule=rule, eps_rel=eps_rel, eps_p=-1.0, eps_r=-1.0, eps_e=-1.0, max_it=int(max_it),
+                     callback_every=0, rhs_on_device=0, keep_x_on_device=0, iters_per_graph=int(iters_per_graph),
+                     small_grid_path=int(small_grid_path), single_sweep=int(single_sweep),
+                     preconditioner=int(preconditioner))
+        for a in list(bs) + list(xs):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == (self.n_local,)
+        bp = (C.c_void_p * max(count, 1))(*[a.ctypes.data for a in bs])
+        xp = (C.c_void_p * max(count, 1))(*[a.ctypes.data for a in xs])
+        infos = (SolveInfo * max(count, 1))()
+        cb = BATCH_CB(lambda _user, i, info: done(i, info.contents.as_dict())) if done is not None else None
+        flag_ptr = None if stop_flag is None else C.cast(C.byref(stop_flag), C.c_void_p)
+        check(self.L.b200cg_solve_batch(self.h, C.byref(prm), count, bp, xp, infos,
+                                        C.cast(cb, C.c_void_p) if cb else None, None, flag_ptr))
+        return [infos[i].as_dict() for i in range(count)]
 
     def cta_times(self, flavour):
         """(start_ns, end_ns) of every persistent CTA in the last launch of a sweep-kernel flavour (diagnostics)."""

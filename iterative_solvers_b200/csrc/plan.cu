@@ -382,6 +382,15 @@ static void free_plan(b200cg_plan_s* P) {
   cudaFree(P->va);
   cudaFree(P->vb);
   cudaFree(P->compact);
+  if (P->batch) {
+    BatchIo* io = P->batch;
+    if (io->s_in) cudaStreamDestroy(io->s_in);
+    if (io->s_out) cudaStreamDestroy(io->s_out);
+    cudaFree(io->stage_out);
+    for (cudaEvent_t e : {io->h2d_done, io->in_free, io->gathered, io->d2h_done[0], io->d2h_done[1]})
+      if (e) cudaEventDestroy(e);
+    delete io;
+  }
   cudaFree(P->d_state);
   cudaFree(P->d_log);
   cudaFree(P->d_partials);

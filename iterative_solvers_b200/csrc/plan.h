@@ -74,6 +74,16 @@ struct TileTable {  // one per sweep flavour: 0 = dot phase, 1 = update without 
   std::vector<double> weight;  // relative share of the sweep per CTA
 };
 
+// b200cg_solve_batch: what overlaps the copies of neighbouring solves with the iterations of the current one (lazy)
+struct BatchIo {
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D of the next right-hand side / D2H of the previous solution
+  double* stage_out = nullptr;                   // second compact staging buffer (P->compact stages the inputs)
+  cudaEvent_t h2d_done = nullptr;                // the next rhs has landed in P->compact
+  cudaEvent_t in_free = nullptr;                 // P->compact has been scattered into P->b
+  cudaEvent_t gathered = nullptr;                // the solution has been gathered into stage_out
+  cudaEvent_t d2h_done[2] = {nullptr, nullptr};  // solution i is complete in host memory (slot i & 1)
+};
+
 }  // namespace b200cg
 
 using namespace b200cg;  // internal header: the plan struct is the C ABI's opaque type and lives at global scope
@@ -134,6 +144,7 @@ struct b200cg_plan_s {
   unsigned long long* d_peer_trace = nullptr;  // B200CG_PEER_TRACE=1: stamps of the single sweep's cross-rank step
   int64_t n_global = 0;
   std::vector<int> ycuts;  // row cuts of all ranks
+  BatchIo* batch = nullptr;   // copy streams / staging of b200cg_solve_batch (created by its first call)
   MgHierarchy* mg = nullptr;  // level hierarchy of the opt-in multigrid preconditioner (built by the first solve that asks)
 };
 

@@ -215,6 +215,14 @@ static int default_iters_per_graph(const b200cg_plan_s* P) {
   return std::max(20, std::min(200, k & ~1));
 }
 
+// One solve of a b200cg_solve_batch queue: its right-hand side is already on its way into P->compact on the input copy
+// stream, the next one follows as soon as the staging buffer is free, the solution leaves on the output copy stream.
+struct BatchStep {
+  BatchIo* io;
+  const double* next_b;  // right-hand side of the following solve (nullptr: none)
+  int index;
+};
+
 // Everything one b200cg_solve call carries between its phases.
 struct SolveCall {
   b200cg_plan_s* P;
@@ -229,6 +237,7 @@ struct SolveCall {
   double dot_ms = 0.0, upd_even_ms = 0.0, upd_odd_ms = 0.0;
   int samples = 0;
   long long count;  // unknowns of this rank
+  const BatchStep* batch = nullptr;
 };
 
 static int check_solve_args(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, double* x_host,
@@ -273,7 +282,22 @@ static int upload_inputs(SolveCall& c, const double* b_host, const double* u_hos
     }
     P->csr.has_u = c.with_u;
   } else {
-    if (!c.prm->rhs_on_device) {
+    if (c.batch) {
+      // the copy was enqueued on the input copy stream while the previous solve iterated
+      BatchIo* io = c.batch->io;
+      CU(cudaStreamWaitEvent(s, io->h2d_done, 0));
+      scatter_compact_kernel<<<ew_grid(P, c.count), CTA_THREADS, 0, s>>>(P->compact, P->b, P->g);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(io->in_free, s));
+      if (c.batch->next_b) {
+        CU(cudaStreamWaitEvent(io->s_in, io->in_free, 0));
+        CU(cudaMemcpyAsync(P->compact, c.batch->next_b, bytes, cudaMemcpyHostToDevice, io->s_in));
+        CU(cudaEventRecord(io->h2d_done, io->s_in));
+      }
+      P->have_rhs = true;
+      c.info->h2d_bytes += bytes;
+      c.info->kernel_launches += 1;
+    } else if (!c.prm->rhs_on_device) {
       RET(upload_vector(P, b_host, P->b));
       P->have_rhs = true;
       c.info->h2d_bytes += bytes;
@@ -558,7 +582,21 @@ static int collect_solution(SolveCall& c, const DevState& st, double* x_host) {
     c.info->kernel_launches += 1;
   }
   P->solution_in_csr = c.csr;
-  if (!c.prm->keep_x_on_device) {
+  if (c.batch) {
+    // gather into the second staging buffer once the previous solution has left it; the copy to the host runs on the
+    // output copy stream under the next solve's iterations
+    BatchIo* io = c.batch->io;
+    const int i = c.batch->index;
+    if (i > 0) CU(cudaStreamWaitEvent(s, io->d2h_done[(i - 1) & 1], 0));
+    gather_compact_kernel<<<ew_grid(P, c.count), CTA_THREADS, 0, s>>>(P->x, io->stage_out, P->g);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(io->gathered, s));
+    CU(cudaStreamWaitEvent(io->s_out, io->gathered, 0));
+    CU(cudaMemcpyAsync(x_host, io->stage_out, c.count * sizeof(double), cudaMemcpyDeviceToHost, io->s_out));
+    CU(cudaEventRecord(io->d2h_done[i & 1], io->s_out));
+    c.info->kernel_launches += 1;
+    c.info->d2h_bytes += c.count * (int64_t)sizeof(double);
+  } else if (!c.prm->keep_x_on_device) {
     if (c.csr) {
       CU(cudaMemcpyAsync(x_host, P->csr.x, c.count * sizeof(double), cudaMemcpyDeviceToHost, s));
     } else {
@@ -602,9 +640,9 @@ static void fill_info(const SolveCall& c, const DevState& st) {
   info->peer_exchange = (P->desc.world > 1 && P->peer_mode && !c.report && !c.use_cluster) ? 1 : 0;
 }
 
-extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
-                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
-                            const volatile int* stop_flag) {
+static int solve_impl(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
+                      double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user, const volatile int* stop_flag,
+                      const BatchStep* batch) {
   RET(check_solve_args(P, prm, b_host, x_host, info, cb));
   memset(info, 0, sizeof(*info));
   const double t_begin = now_ms();
@@ -614,6 +652,7 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
               /*csr=*/prm->op == B200CG_OP_CSR, /*with_u=*/u_host != nullptr,
               /*report=*/prm->rule == B200CG_RULE_REL_L2 && cb != nullptr};
   c.count = local_count(P);
+  c.batch = batch;
   info->local_unknowns = c.count;
   P->have_solution = false;
 
@@ -666,6 +705,71 @@ extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const dou
   if (cb && prm->rule == B200CG_RULE_MAXNORM) cb(user, st.it, st.dx_max, st.r_max, st.err_max);
   info->total_ms = now_ms() - t_begin;
   return B200CG_OK;
+}
+
+extern "C" int b200cg_solve(b200cg_plan_t P, const b200cg_params* prm, const double* b_host, const double* u_host,
+                            double* x_host, b200cg_info* info, b200cg_iter_cb cb, void* user,
+                            const volatile int* stop_flag) {
+  return solve_impl(P, prm, b_host, u_host, x_host, info, cb, user, stop_flag, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------- batch of right-hand sides
+static int batch_io(b200cg_plan_s* P, BatchIo** out) {
+  if (!P->batch) P->batch = new BatchIo();
+  BatchIo* io = P->batch;
+  if (!io->s_in) CU(cudaStreamCreateWithFlags(&io->s_in, cudaStreamNonBlocking));
+  if (!io->s_out) CU(cudaStreamCreateWithFlags(&io->s_out, cudaStreamNonBlocking));
+  if (!io->stage_out) CU(cudaMalloc(&io->stage_out, std::max<long long>(local_count(P), 1) * sizeof(double)));
+  for (cudaEvent_t* e : {&io->h2d_done, &io->in_free, &io->gathered, &io->d2h_done[0], &io->d2h_done[1]})
+    if (!*e) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  *out = io;
+  return B200CG_OK;
+}
+
+extern "C" int b200cg_solve_batch(b200cg_plan_t P, const b200cg_params* prm, int count, const double* const* b_hosts,
+                                  double* const* x_hosts, b200cg_info* infos, b200cg_batch_cb done, void* user,
+                                  const volatile int* stop_flag) {
+  if (!P || !prm || count < 0 || (count > 0 && (!b_hosts || !x_hosts || !infos)))
+    return fail(B200CG_ERR_INVALID_ARG, "plan/params/b_hosts/x_hosts/infos is NULL or count < 0");
+  if (prm->op != B200CG_OP_MATRIX_FREE) return fail(B200CG_ERR_UNSUPPORTED, "b200cg_solve_batch serves the matrix-free operator");
+  if (prm->rhs_on_device || prm->keep_x_on_device)
+    return fail(B200CG_ERR_INVALID_ARG, "b200cg_solve_batch moves every rhs and every solution: rhs_on_device / keep_x_on_device must be 0");
+  NEED_GEOMETRY(P);
+  for (int i = 0; i < count; ++i)
+    if (!b_hosts[i] || !x_hosts[i]) return fail(B200CG_ERR_INVALID_ARG, "b_hosts[%d] / x_hosts[%d] is NULL", i, i);
+  if (count == 0) return B200CG_OK;
+  CU(cudaSetDevice(P->desc.device));
+  BatchIo* io = nullptr;
+  RET(batch_io(P, &io));
+  memset(infos, 0, sizeof(b200cg_info) * (size_t)count);
+  const size_t bytes = (size_t)local_count(P) * sizeof(double);
+  // (anything an earlier call left in the staging buffers has been consumed: every entry point ends synchronised)
+  int rc = B200CG_OK;
+  auto cuda_ok = [&](cudaError_t e, const char* what) {
+    if (e == cudaSuccess || rc != B200CG_OK) return;
+    rc = fail(B200CG_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+  };
+  cuda_ok(cudaMemcpyAsync(P->compact, b_hosts[0], bytes, cudaMemcpyHostToDevice, io->s_in), "H2D of the first right-hand side");
+  cuda_ok(cudaEventRecord(io->h2d_done, io->s_in), "cudaEventRecord");
+  int solved = 0;
+  for (int i = 0; i < count && rc == B200CG_OK; ++i) {
+    const BatchStep step{io, i + 1 < count ? b_hosts[i + 1] : nullptr, i};
+    rc = solve_impl(P, prm, b_hosts[i], nullptr, x_hosts[i], &infos[i], nullptr, nullptr, stop_flag, &step);
+    if (rc != B200CG_OK) break;
+    ++solved;
+    if (i > 0) {  // solution i-1 left under this solve's iterations
+      cuda_ok(cudaEventSynchronize(io->d2h_done[(i - 1) & 1]), "D2H of a solution");
+      if (rc == B200CG_OK && done) done(user, i - 1, &infos[i - 1]);
+    }
+    if (infos[i].stop_reason == B200CG_STOP_INTERRUPTED) break;  // requestStop ends the queue with this solve
+  }
+  // nothing may stay in flight on the caller's buffers, whatever happened
+  const cudaError_t e_in = cudaStreamSynchronize(io->s_in), e_out = cudaStreamSynchronize(io->s_out);
+  cuda_ok(e_in, "input copy stream");
+  cuda_ok(e_out, "output copy stream");
+  if (rc == B200CG_OK && solved > 0 && done) done(user, solved - 1, &infos[solved - 1]);
+  for (int i = solved; i < count; ++i) infos[i].stop_reason = B200CG_STOP_INTERRUPTED;
+  return rc;
 }
 
 extern "C" int b200cg_get_solution(b200cg_plan_t P, double* x_host) {

@@ -341,6 +341,38 @@ std::vector<double> MatrixFreeSolver::solve(const std::vector<double>& true_solu
   return x;
 }
 
+std::vector<std::vector<double>> MatrixFreeSolver::solveBatch(const std::vector<std::vector<double>>& right_hand_sides,
+                                                             std::vector<int>* iterations_out) {
+  const size_t rows = static_cast<size_t>(system.size()), count = right_hand_sides.size();
+  std::vector<std::vector<double>> xs(count, std::vector<double>(rows));
+  std::vector<const double*> b_ptrs(count);
+  std::vector<double*> x_ptrs(count);
+  for (size_t i = 0; i < count; ++i) {
+    if (right_hand_sides[i].size() != rows) throw std::invalid_argument("MatrixFreeSolver::solveBatch: a right-hand side has the wrong length");
+    b_ptrs[i] = right_hand_sides[i].data();
+    x_ptrs[i] = xs[i].data();
+  }
+  b200cg_params prm = {};
+  prm.op = B200CG_OP_MATRIX_FREE;
+  prm.rule = B200CG_RULE_REL_L2;
+  prm.eps_rel = eps;
+  prm.max_it = maxIterations;
+  prm.preconditioner = multigrid ? B200CG_PRECOND_MULTIGRID : B200CG_PRECOND_NONE;
+  std::vector<b200cg_info> infos(count);
+  check(b200cg_solve_batch(system.plan()->get(), &prm, static_cast<int>(count), b_ptrs.data(), x_ptrs.data(), infos.data(),
+                           nullptr, nullptr, nullptr));
+  if (iterations_out) iterations_out->assign(count, 0);
+  for (size_t i = 0; i < count; ++i) {
+    iterations = infos[i].iterations;
+    last_solve_ms = infos[i].solve_ms;
+    if (iterations_out) (*iterations_out)[i] = infos[i].iterations;
+    const bool ok = infos[i].converged != 0;
+    if (completion_callback)
+      completion_callback(ok, ok ? "Converged successfully" : "Failed to converge within maximum iterations");
+  }
+  return xs;
+}
+
 // ------------------------------------------------------------------------------------------------- facade
 DirichletSolver::DirichletSolver(int n, int m, double a, double b, double c, double d)
     : n_internal(n), m_internal(m), a_bound(a), b_bound(b), c_bound(c), d_bound(d),

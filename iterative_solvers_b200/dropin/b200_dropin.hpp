@@ -239,6 +239,11 @@ class MatrixFreeSolver {
   // B200 additions: device timing of the last solve; opt-in multigrid preconditioner (no per-iteration callback then)
   double lastSolveMilliseconds() const { return last_solve_ms; }
   void enableMultigridPreconditioner(bool enable) { multigrid = enable; }
+  // B200 addition: solve() once per entry of right_hand_sides (the constructor's b is not used), same results, as ONE
+  // queue whose host copies overlap the iterations (b200cg_solve_batch). No per-iteration callback; the completion
+  // callback fires once per solve; getIterations() reports the last solve, iterations_out every one.
+  std::vector<std::vector<double>> solveBatch(const std::vector<std::vector<double>>& right_hand_sides,
+                                              std::vector<int>* iterations_out = nullptr);
 
  private:
   bool multigrid = false;

@@ -114,6 +114,31 @@ int cmd_mf(char** a) {
   return 0;
 }
 
+// MatrixFreeSolver::solveBatch (B200 addition): three scaled copies of the system's rhs through the queue, next to solve()
+int cmd_mfbatch(char** a) {
+  const int n = std::atoi(a[0]);
+  const double lo = std::atof(a[1]), hi = std::atof(a[2]), eps = std::atof(a[3]);
+  const int max_it = std::atoi(a[4]);
+  MatrixFreeSystem system(n, n, lo, hi, lo, hi);
+  std::vector<std::vector<double>> rhs(3, system.get_rhs());
+  for (double& v : rhs[1]) v *= -2.0;
+  for (double& v : rhs[2]) v *= 0.5;
+  MatrixFreeSolver solver(system, system.get_rhs(), eps, max_it);
+  int completions = 0;
+  solver.setCompletionCallback([&](bool ok, const std::string&) { completions += ok ? 1 : 100; });
+  std::vector<int> its;
+  std::vector<std::vector<double>> xs = solver.solveBatch(rhs, &its);
+  std::vector<double> single = solver.solve(std::vector<double>());
+  dump("x0.bin", xs[0]);
+  dump("x1.bin", xs[1]);
+  dump("x2.bin", xs[2]);
+  dump("x_single.bin", single);
+  std::ofstream info(g_out + "/info.txt");
+  info << "iterations=" << its[0] << " " << its[1] << " " << its[2] << "\nsingle_iterations=" << solver.getIterations()
+       << "\ncompletions=" << completions << "\n";
+  return 0;
+}
+
 // the opt-in multigrid-preconditioned CG through both doors: the Solver subclass on a GridSystem and the switch of
 // MatrixFreeSolver
 int cmd_mgpcg(char** a) {
@@ -296,7 +321,7 @@ int cmd_stop(char** a) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|grid|mgpcg|errors|io|stop> <args...> <outdir>\n");
+    std::fprintf(stderr, "usage: dropin_test <dirichlet|mf|mfbatch|grid|mgpcg|errors|io|stop> <args...> <outdir>\n");
     return 2;
   }
   g_out = argv[argc - 1];
@@ -306,6 +331,7 @@ int main(int argc, char** argv) {
     if (cmd == "mf" && argc == 9) return cmd_mf(argv + 2);
     if (cmd == "grid" && argc == 10) return cmd_grid(argv + 2);
     if (cmd == "mgpcg" && argc == 8) return cmd_mgpcg(argv + 2);
+    if (cmd == "mfbatch" && argc == 8) return cmd_mfbatch(argv + 2);
     if (cmd == "errors") return cmd_errors(argv + 2);
     if (cmd == "io" && argc == 3) return cmd_io(argv + 2);
     if (cmd == "stop" && argc == 4) return cmd_stop(argv + 2);

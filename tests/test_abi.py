@@ -89,6 +89,19 @@ def test_no_cpu_fallback(capi):
     assert "no" in str(e.value).lower()
 
 
+def test_solve_batch_validates_its_arguments_without_a_device(capi):
+    """b200cg_solve_batch rejects a NULL plan / negative count before it touches CUDA."""
+    import ctypes as C
+
+    L = capi.lib()
+    prm = capi.Params(op=capi.OP_MATRIX_FREE, rule=capi.RULE_REL_L2, eps_rel=1e-8, max_it=10)
+    info = (capi.SolveInfo * 1)()
+    ptrs = (C.c_void_p * 1)()
+    assert L.b200cg_solve_batch(None, C.byref(prm), 1, ptrs, ptrs, info, None, None, None) == 1
+    assert b"NULL" in L.b200cg_last_error()
+    assert L.b200cg_solve_batch(None, C.byref(prm), -1, ptrs, ptrs, info, None, None, None) == 1
+
+
 def test_product_does_not_reach_into_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/."""
     pkg = os.path.join(ROOT, "iterative_solvers_b200")

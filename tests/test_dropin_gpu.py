@@ -217,3 +217,23 @@ def test_multigrid_pcg_behind_the_solver_interface(driver, tmp_path, oracle_mod)
     plain = o.mf_solve(b=b, eps=1e-10, max_it=20000)
     assert relmax(x, plain["x"]) < 1e-7
     assert float(i["r"]) <= 1e-8 * float(i["r0"])
+
+
+@pytest.mark.gpu
+def test_matrix_free_solver_batch(driver, tmp_path, golden_ref):
+    """MatrixFreeSolver::solveBatch (B200 addition, b200cg_solve_batch): three scaled right-hand sides through the queue.
+    The scales are powers of two, under which every operation of CG scales exactly: all three take the reference's
+    iteration count for this grid and give the scaled solution; the first equals solve() on the same system."""
+    n = 64
+    run(driver, "mfbatch", n, 0, 1, 1e-8, 10000, tmp_path)
+    i = info(tmp_path)
+    ref_x = golden_ref[f"mf_n{n}_a0_x"]
+    ref_it = int(golden_ref[f"mf_n{n}_a0_iters"][0])
+    its = [int(t) for t in i["iterations"].split()]
+    assert its == [ref_it] * 3 and int(i["single_iterations"]) == ref_it
+    assert int(i["completions"]) == 4  # three from the queue, one from solve(), all converged
+    assert relmax(f64(tmp_path, "x0.bin"), ref_x) < REL
+    assert relmax(f64(tmp_path, "x_single.bin"), ref_x) < REL
+    assert np.array_equal(f64(tmp_path, "x0.bin"), f64(tmp_path, "x_single.bin"))
+    assert relmax(f64(tmp_path, "x1.bin"), -2.0 * f64(tmp_path, "x0.bin")) < 1e-12
+    assert relmax(f64(tmp_path, "x2.bin"), 0.5 * f64(tmp_path, "x0.bin")) < 1e-12
