@@ -108,13 +108,15 @@ typedef struct {
   int small_grid_path;     /* grids that fit the shared memory of one thread-block cluster (about 300^2) are solved by
                               a single cluster-resident kernel instead of the graph loop: 0 = automatic, 1 = never,
                               2 = require it (B200CG_ERR_UNSUPPORTED if the grid does not fit) */
-  int single_sweep;        /* matrix-free, RULE_REL_L2, no callback: each iteration runs as ONE sweep (40 instead of 56 bytes
-                              per unknown) by forming alpha from the single-reduction CG recurrence (Chronopoulos-Gear)
-                              instead of p.Ap - the same iterates in exact arithmetic, <= 4e-14 relative apart in fp64 on
-                              the reference's grids (tests/studies/single_reduction_cg.py), same iteration counts. On
-                              sharded plans it needs the peer-memory exchange and >= 4 rows per rank. 0 = the plan's
-                              default (on unless B200CG_SINGLE_SWEEP=0), 1 = on, 2 = never (the two-sweep iteration with
-                              alpha = r.r / p.Ap). Ignored where it does not apply */
+  int single_sweep;        /* matrix-free operator: each iteration runs as ONE sweep by forming alpha from the single-reduction CG
+                              recurrence (Chronopoulos-Gear) instead of p.Ap - the same iterates in exact arithmetic, <= 4e-14
+                              relative apart in fp64 on the reference's grids (tests/studies/single_reduction_cg.py), same
+                              iteration counts. RULE_REL_L2 without a callback: 40 instead of 56 bytes per unknown-iteration; on
+                              sharded plans it needs the peer-memory exchange and >= 4 rows per rank. RULE_MAXNORM (MSGSolver's
+                              rules, callbacks included) on a single-GPU plan: 48 (56 with u) instead of 64 (72) bytes, r.z
+                              replaced by r.r of the same residual. 0 = the plan's default (on unless B200CG_SINGLE_SWEEP=0),
+                              1 = on, 2 = never (dot sweep + update sweep with alpha = r.r / p.Ap resp. r.z / Az.z). Ignored
+                              where it does not apply (assembled operator, per-iteration report, MAXNORM on sharded plans) */
   int preconditioner;      /* b200cg_preconditioner. B200CG_PRECOND_MULTIGRID (opt-in; the reference has no preconditioner,
                               solver.hpp:17-66 is the base class kept for one): CG preconditioned by a geometric-multigrid
                               V-cycle - matrix-free operator, RULE_REL_L2, no callback, single-GPU plan; the iteration
@@ -149,7 +151,7 @@ typedef struct {
   int cluster_path;        /* 1 if this solve ran as one cluster-resident kernel (small_grid_path) */
   int peer_exchange;       /* sharded plans: 1 if halo rows and reductions went over NVLink peer memory (CUDA IPC),
                               0 if over NCCL send/recv + all-reduce */
-  int single_sweep;        /* 1 if this solve ran the single-sweep iteration (b200cg_params.single_sweep) */
+  int single_sweep;        /* 1 if this solve ran the single-sweep iteration (b200cg_params.single_sweep), under either rule */
   int preconditioner;      /* b200cg_preconditioner this solve ran with */
   int mg_levels;           /* multigrid levels used (0 without the preconditioner) */
 } b200cg_info;

@@ -37,15 +37,23 @@ constexpr int FUSED_STRIP_OUT = fused_strip_out(FUSED_CW);
 template <int FLAGS>
 struct FusedCfg {
   static constexpr bool X2 = (FLAGS & F_X2) != 0;   // odd iteration: x += alpha_prev * p_old + alpha * p
-  static constexpr bool NOX = !X2;                  // even iteration: x untouched, its update stays pending
-  static constexpr int NSTREAM = X2 ? 3 : 2;        // p, r, [x]
+  // F_MAXN (MSGSolver's max-norm rules, msg_solver.cpp:105-162): x += alpha * p EVERY iteration and the sweep also
+  // reduces |r'|_inf, |x' - x|_inf and, with F_U, |x' - u|_inf - the rules look at them after every iteration, so there
+  // is no x-deferral: 48 B per unknown-iteration (56 with u) against 64 (72) of the dot sweep + update sweep
+  static constexpr bool MAXN = (FLAGS & F_MAXN) != 0;
+  static constexpr bool XS = X2 || MAXN;            // x is streamed (emit rows only)
+  static constexpr bool LOAD_U = MAXN && (FLAGS & F_U) != 0;  // so is the true solution
+  static constexpr int NSTREAM = 2 + (XS ? 1 : 0) + (LOAD_U ? 1 : 0);  // p, r, [x], [u]
   static constexpr int NS = 2;                      // gamma' = r'.r', delta' = r'.A r'
+  static constexpr int NM = MAXN ? (LOAD_U ? 3 : 2) : 0;  // |r'|_inf, |dx|_inf, [|x' - u|_inf]'
   static constexpr int ROWS_BELOW = 2;              // rows streamed below a tile's first emit row
   // F_SHARD (sharded plans, peer memory): the slab's two first / last rows of r' and p also go to the neighbours - into
   // their halo row and into one of the two extra rows every pitched vector carries behind its stored rows (row ylo-2 at
   // index yrows, row yhi+1 at index yrows+1) - and the iteration's two sums cross the ranks through the PeerSync slots,
   // alternating the slot by iteration parity: ONE publish-and-wait per iteration.
   static constexpr bool SHARD = (FLAGS & F_SHARD) != 0;
+  static_assert(!(SHARD && MAXN), "the max-norm flavour of the single sweep serves single-GPU plans");
+  static_assert(!(X2 && MAXN), "x-deferral and the max-norm rules exclude each other");
 };
 
 template <int FLAGS, int HS, int NST, int CW>
@@ -79,14 +87,47 @@ __device__ __forceinline__ void finalize_fused(DevState* st, double gamma_new, d
   st->pAp = gamma_new / alpha;
 }
 
+// The same for MSGSolver's rules (msg_solver.cpp:115-183): the three max-norm tests in the reference's order, then
+// beta = (|r'|_2)^2 / r.z with r.z = gamma of the previous iteration (r.z = r.r in exact arithmetic: z - r is a multiple
+// of the previous direction, to which r is orthogonal) and alpha from the single-reduction recurrence.
+__device__ __forceinline__ void finalize_fused_maxnorm(DevState* st, CbRecord* log, double gamma_new, double delta_new,
+                                                       double r_max, double dx_max, double err_max) {
+  const int it = st->it + 1;
+  st->it = it;
+  const double r_norm = sqrt(gamma_new);
+  st->r_norm = r_norm;
+  st->r_max = r_max;
+  st->dx_max = dx_max;
+  if (st->has_u) st->err_max = err_max;
+  st->x_pending = 0;
+  int done = 0;
+  if (st->eps_p > 0 && dx_max < st->eps_p) { done = 1; st->converged = 1; st->stop_reason = 1; }
+  else if (st->eps_r > 0 && r_max < st->eps_r) { done = 1; st->converged = 1; st->stop_reason = 2; }
+  else if (st->eps_e > 0 && st->has_u && err_max < st->eps_e) { done = 1; st->converged = 1; st->stop_reason = 3; }
+  if (!done) {
+    const double beta = (r_norm * r_norm) / st->rz;
+    const double alpha = gamma_new / (delta_new - beta * gamma_new / st->alpha);
+    st->rz = gamma_new;
+    st->rr = gamma_new;
+    st->beta = beta;
+    st->alpha = alpha;
+    st->pAp = gamma_new / alpha;
+    if (st->callback_every > 0 && (it % st->callback_every == 0 || it == 1))
+      append_record(st, log, (double)it, dx_max, r_max, st->err_max);
+    if (it >= st->max_it) { done = 1; st->converged = 0; st->stop_reason = 0; }
+  }
+  st->done = done;
+}
+
 template <int FLAGS, int HS, int NST, int CW = FUSED_CW>
 __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fused_kernel(const TileArgs a) {
   constexpr int FUSED_ROW = fused_row(CW), FUSED_STRIP_COLS = fused_row(CW);
   using Cfg = FusedCfg<FLAGS>;
-  constexpr bool X2 = Cfg::X2, SHARD = Cfg::SHARD;
-  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, LO = Cfg::ROWS_BELOW;
+  constexpr bool X2 = Cfg::X2, SHARD = Cfg::SHARD, MAXN = Cfg::MAXN, XS = Cfg::XS, LOAD_U = Cfg::LOAD_U;
+  constexpr int NSTREAM = Cfg::NSTREAM, NS = Cfg::NS, NM = Cfg::NM, LO = Cfg::ROWS_BELOW;
   constexpr int STAGE_DOUBLES = HS * NSTREAM * FUSED_ROW;
-  constexpr int OFF_P = 0, OFF_R = HS * FUSED_ROW, OFF_X = 2 * HS * FUSED_ROW;
+  constexpr int OFF_P = 0, OFF_R = HS * FUSED_ROW, OFF_X = 2 * HS * FUSED_ROW, OFF_U = 3 * HS * FUSED_ROW;
+  constexpr int MI_DX = NM > 1 ? 1 : 0, MI_E = NM > 0 ? NM - 1 : 0;  // slots of |dx|_inf and |x' - u|_inf in acc_m
 
   const Geom& g = a.g;
   DevState* st = a.st;
@@ -97,7 +138,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE_DOUBLES * 8);
   uint64_t* empty = full + NST;
   StageMeta* meta = reinterpret_cast<StageMeta*>(empty + NST);
-  __shared__ double scratch[NS * 32];
+  __shared__ double scratch[(NS + NM) * 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -111,7 +152,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
   __syncthreads();
 
   double acc_s[NS] = {0.0};  // gamma', delta'
-  double acc_m[1] = {0.0};
+  double acc_m[NM > 0 ? NM : 1] = {0.0};  // F_MAXN: |r'|_inf, |dx|_inf, [|x' - u|_inf]
   bool sent_halo = false;  // F_SHARD: this thread stored into a neighbour rank's rows
   const int y_store_lo = g.ybase, y_store_hi = g.ybase + g.yrows;  // stored rows [lo, hi)
   // Row index of grid row y inside a pitched vector, or -1 where the row does not exist (beyond the domain boundary).
@@ -150,7 +191,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
             stored += (row_index(y) >= 0) ? 1 : 0;
             inner += (y >= ya && y < yb) ? 1 : 0;
           }
-          const uint32_t bytes = row_bytes * (uint32_t)(2 * stored + (X2 ? inner : 0));
+          const uint32_t bytes = row_bytes * (uint32_t)(2 * stored + (XS ? inner : 0) + (LOAD_U ? inner : 0));
           mbar_arrive_expect_tx(&full[stage], bytes);
           double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
           for (int j = 0; j < nrows; ++j) {
@@ -160,7 +201,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
             const size_t off = (size_t)ri * pitch + (size_t)col0;
             bulk_g2s(sd + OFF_P + j * FUSED_ROW, a.p_in + off, row_bytes, &full[stage]);
             bulk_g2s(sd + OFF_R + j * FUSED_ROW, a.r_in + off, row_bytes, &full[stage]);
-            if (X2 && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * FUSED_ROW, a.x + off, row_bytes, &full[stage]);
+            if (XS && y >= ya && y < yb) bulk_g2s(sd + OFF_X + j * FUSED_ROW, a.x + off, row_bytes, &full[stage]);
+            if (LOAD_U && y >= ya && y < yb) bulk_g2s(sd + OFF_U + j * FUSED_ROW, a.u + off, row_bytes, &full[stage]);
           }
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
@@ -203,10 +245,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
     double2 R1 = zero2, R2 = zero2;        // r' of rows y-2, y-3
     double LR1 = 0.0, RR1 = 0.0;           // horizontal neighbours of R1
     double2 r1 = zero2, x1 = zero2, q1 = zero2;  // staged r, x, p_old of row y-1 (masked)
+    double2 u1 = zero2;                    // F_U: staged true solution of row y-1
     bool k1a = false, k1b = false;         // row y-1: are this thread's two nodes unknowns
     bool va = false, vb = false;           // the same for the rows of the tile itself (all in one block of the L)
     bool warp_on = true;                   // this warp writes at least one unknown of the tile
     bool st_ok = false;                    // this thread stores in the tile's rows (a writer lane with an unknown)
+    bool ma = false, mb = false;           // this thread's two nodes enter the maxima of the tile's rows (writer && va / vb)
 
     for (;;) {
       mbar_wait(&full[stage], phase);
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
         yb = m.yb;
         x0 = m.col0 + sc - XOFF;
         col_off = (size_t)(m.col0 + sc);
-        P1 = P2 = R1 = R2 = r1 = x1 = q1 = zero2;
+        P1 = P2 = R1 = R2 = r1 = x1 = q1 = u1 = zero2;
         LP1 = RP1 = LR1 = RR1 = 0.0;
         k1a = k1b = false;
         va = (x0 >= m.xlo) && (x0 <= g.n - 1);
@@ -229,6 +273,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
         const int xw = m.col0 + FUSED_WARP_STEP * warp - XOFF;  // node of the window's first staged column
         warp_on = (xw + 61 >= m.xlo) && (xw + 2 <= g.n - 1);
         st_ok = writer && (va || vb);
+        ma = writer && va;
+        mb = writer && vb;
       }
       const double* sd = stage_data + (size_t)stage * STAGE_DOUBLES;
       // One staged row. full_tag: every row of the stage lies in [ya+2, yb), so it is stored, it is a row of the
@@ -241,13 +287,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
         const int y = m.y0 + j;
         // ---- row y arrives: its direction p = r + beta * p_old, zero outside the unknowns
         bool k0a, k0b;
-        double2 cur_p = zero2, cur_r = zero2, cur_x = zero2;
+        double2 cur_p = zero2, cur_r = zero2, cur_x = zero2, cur_u = zero2;
         if (FULL) {
           k0a = va;
           k0b = vb;
           cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
           cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
-          if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+          if (XS) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+          if (LOAD_U) cur_u = *reinterpret_cast<const double2*>(sd + OFF_U + j * FUSED_ROW + sc);
         } else {
           const bool row_stored = row_index(y) >= 0;
           const bool row_ok = (y >= 1) && (y <= g.m - 1);
@@ -257,11 +304,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
           if (row_stored) {
             cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
             cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
-            if (X2 && y >= ya && y < yb) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+            if (XS && y >= ya && y < yb) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+            if (LOAD_U && y >= ya && y < yb) cur_u = *reinterpret_cast<const double2*>(sd + OFF_U + j * FUSED_ROW + sc);
           }
           cur_p.x = k0a ? cur_p.x : 0.0;  cur_p.y = k0b ? cur_p.y : 0.0;
           cur_r.x = k0a ? cur_r.x : 0.0;  cur_r.y = k0b ? cur_r.y : 0.0;
           cur_x.x = k0a ? cur_x.x : 0.0;  cur_x.y = k0b ? cur_x.y : 0.0;
+          cur_u.x = k0a ? cur_u.x : 0.0;  cur_u.y = k0b ? cur_u.y : 0.0;
         }
         double2 P0;
         P0.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
@@ -279,10 +328,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
         }
         const bool emit1 = FULL || ((y - 1 >= ya) && (y - 1 < yb));
         if (emit1 && writer) {
+          double2 xm = zero2;  // F_MAXN: x' = x + alpha * p (msg_solver.cpp:105-107)
+          if (MAXN) {
+            xm.x = __dadd_rn(x1.x, __dmul_rn(alpha, P1.x));
+            xm.y = __dadd_rn(x1.y, __dmul_rn(alpha, P1.y));
+          }
           if (k1a || k1b) {
             const size_t o = (size_t)(y - 1 - g.ybase) * pitch + col_off;
             st2_out(a.r_out + o, R0);
             st2_out(a.p_out + o, P1);
+            if (MAXN) st2_out(a.x + o, xm);
             if (X2) {  // x += alpha_prev * p_old, then += alpha * p: the reference's order of additions
               double2 xn;
               xn.x = __dadd_rn(__dadd_rn(x1.x, __dmul_rn(alpha_prev, q1.x)), __dmul_rn(alpha, P1.x));
@@ -310,6 +365,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
           }
           acc_s[0] = fma(R0.x, R0.x, acc_s[0]);
           acc_s[0] = fma(R0.y, R0.y, acc_s[0]);
+          if (MAXN) {
+            // |r'|_inf, |x' - x|_inf, |x' - u|_inf over the unknowns (msg_solver.cpp:121-139); after a FULL stage x1 / u1 are
+            // unmasked, hence the selects
+            acc_m[0] = fmax(acc_m[0], fmax(fabs(R0.x), fabs(R0.y)));
+            const double d0 = k1a ? fabs(__dsub_rn(xm.x, x1.x)) : 0.0;
+            const double d1 = k1b ? fabs(__dsub_rn(xm.y, x1.y)) : 0.0;
+            acc_m[MI_DX] = fmax(acc_m[MI_DX], fmax(d0, d1));
+            if (LOAD_U) {
+              const double e0 = k1a ? fabs(__dsub_rn(xm.x, u1.x)) : 0.0;
+              const double e1 = k1b ? fabs(__dsub_rn(xm.y, u1.y)) : 0.0;
+              acc_m[MI_E] = fmax(acc_m[MI_E], fmax(e0, e1));
+            }
+          }
         }
         const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
         const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
@@ -325,7 +393,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
 
         // ---- shift the pipeline
         P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
-        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
+        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;  u1 = cur_u;
         k1a = k0a;  k1b = k0b;
       };
       // The same row for a FULL stage (all but a tile's first and last), written branch-free: the ncu source page of the
@@ -338,8 +406,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
       auto do_row_full = [&](const int j) {
         const double2 cur_p = *reinterpret_cast<const double2*>(sd + OFF_P + j * FUSED_ROW + sc);
         const double2 cur_r = *reinterpret_cast<const double2*>(sd + OFF_R + j * FUSED_ROW + sc);
-        double2 cur_x = zero2;
-        if (X2) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+        double2 cur_x = zero2, cur_u = zero2;
+        if (XS) cur_x = *reinterpret_cast<const double2*>(sd + OFF_X + j * FUSED_ROW + sc);
+        if (LOAD_U) cur_u = *reinterpret_cast<const double2*>(sd + OFF_U + j * FUSED_ROW + sc);
         double2 P0;
         P0.x = __dadd_rn(cur_r.x, __dmul_rn(beta, cur_p.x));
         P0.y = __dadd_rn(cur_r.y, __dmul_rn(beta, cur_p.y));
@@ -355,9 +424,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
           xn.x = __dadd_rn(__dadd_rn(x1.x, __dmul_rn(alpha_prev, q1.x)), __dmul_rn(alpha, P1.x));
           xn.y = __dadd_rn(__dadd_rn(x1.y, __dmul_rn(alpha_prev, q1.y)), __dmul_rn(alpha, P1.y));
         }
+        if (MAXN) {  // x' = x + alpha * p; its distance from x and from u enters the maxima (selects: unmasked inputs)
+          xn.x = __dadd_rn(x1.x, __dmul_rn(alpha, P1.x));
+          xn.y = __dadd_rn(x1.y, __dmul_rn(alpha, P1.y));
+          const double d0 = ma ? fabs(__dsub_rn(xn.x, x1.x)) : 0.0;
+          const double d1 = mb ? fabs(__dsub_rn(xn.y, x1.y)) : 0.0;
+          acc_m[MI_DX] = fmax(acc_m[MI_DX], fmax(d0, d1));
+          if (LOAD_U) {
+            const double e0 = ma ? fabs(__dsub_rn(xn.x, u1.x)) : 0.0;
+            const double e1 = mb ? fabs(__dsub_rn(xn.y, u1.y)) : 0.0;
+            acc_m[MI_E] = fmax(acc_m[MI_E], fmax(e0, e1));
+          }
+        }
         st2_out_if(st_ok, a.r_out + eo, R0);
         st2_out_if(st_ok, a.p_out + eo, P1);
-        if (X2) st2_out_if(st_ok, a.x + eo, xn);
+        if (XS) st2_out_if(st_ok, a.x + eo, xn);
         eo += pitch;
         const double RR0 = __shfl_down_sync(0xffffffffu, R0.x, 1);
         const double LR0 = __shfl_up_sync(0xffffffffu, R0.y, 1);
@@ -370,10 +451,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
         acc_s[0] = fma(G0.y, G0.y, acc_s[0]);
         acc_s[1] = fma(G1.x, w0, acc_s[1]);
         acc_s[1] = fma(G1.y, w1, acc_s[1]);
+        if (MAXN) acc_m[0] = fmax(acc_m[0], fmax(fabs(G0.x), fabs(G0.y)));
         G1 = G0;
         R2 = R1;  R1 = R0;  LR1 = LR0;  RR1 = RR0;
         P2 = P1;  P1 = P0;  LP1 = LP0;  RP1 = RP0;
-        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;
+        r1 = cur_r;  x1 = cur_x;  q1 = cur_p;  u1 = cur_u;
       };
       // (sharded plans: the emit rows ya+1 and yb-2 may be rows the neighbours need, so FULL stays clear of them)
       if (!warp_on) {
@@ -398,10 +480,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
 
   if (tid == 0 && a.cta_clock) a.cta_clock[2 * blockIdx.x + 1] = global_ns();
   if (SHARD && sent_halo) __threadfence_system();  // remote halo stores before the exit ticket
-  if (!grid_reduce<NS, 0>(acc_s, acc_m, a.partials, st, scratch)) return;
+  if (!grid_reduce<NS, NM>(acc_s, acc_m, a.partials, st, scratch)) return;
   bool stop_req = poll_stop(st, a.stop_flag);
   double gamma = acc_s[0];
   double delta = acc_s[1];
+  if (MAXN) {
+    finalize_fused_maxnorm(st, a.cb_log, gamma, delta, acc_m[0], acc_m[MI_DX], LOAD_U ? acc_m[MI_E] : DBL_MAX);
+    apply_stop(st, stop_req);
+    return;
+  }
   if (SHARD) {
     // this rank's two sums to every rank, everyone's back; the slot alternates with the iteration parity so that a fast
     // rank's next publication cannot overwrite values a slow rank is still reading

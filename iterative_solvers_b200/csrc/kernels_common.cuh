@@ -24,6 +24,7 @@ enum {
   F_SUB_B = 4,   // APPLY: out = A v - b
   F_NOX = 8,     // UPD, x-deferral: even iteration, x is not touched (its update stays pending)
   F_X2 = 16,     // UPD, x-deferral: odd iteration, applies the pending update and this one
+  F_MAXN = 32,   // single-sweep kernel under MSGSolver's max-norm rules: x every iteration, |r'|_inf, |dx|_inf, |x-u|_inf
   F_SHARD = 64   // single-sweep kernel on a sharded plan: two halo rows per side over peer memory
 };
 

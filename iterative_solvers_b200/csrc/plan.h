@@ -54,7 +54,7 @@ double now_ms();
 
 // ------------------------------------------------------------------------------------------- plan
 // Graph variants (key of b200cg_plan_s::graphs = variant * 4096 + iterations per graph)
-enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16, V_TIMED = 32 };
+enum { V_U = 1, V_REPORT = 2, V_CSR = 4, V_XDEFER = 8, V_FUSED = 16, V_TIMED = 32, V_MAXN = 64 };
 
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;

@@ -32,7 +32,7 @@ static int timed_first_iteration(int iters) { return iters >= 4 ? 2 : 0; }
 static int build_graph(b200cg_plan_s* P, int variant, int iters, bool timed, GraphEntry* out) {
   cudaStream_t s = P->stream;
   const bool with_u = variant & V_U, report = variant & V_REPORT, csr = variant & V_CSR, xdefer = variant & V_XDEFER;
-  const bool fused = variant & V_FUSED;
+  const bool fused = variant & V_FUSED, maxn = variant & V_MAXN;
   int kernels = 0;
   const int k0 = timed_first_iteration(iters);  // the two iterations whose kernels are bracketed by event nodes
   auto EV = [&](cudaEvent_t e, cudaStream_t st, unsigned int flags) {
@@ -96,7 +96,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, bool timed, Gra
       // phase collapse to zero length)
       if (k == k0) EV(P->ev[1], s, cudaEventRecordExternal);
       if (k == k0 + 1) EV(P->ev[8], s, cudaEventRecordExternal);
-      rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
+      if (maxn) rc = with_u ? launch_fused<F_MAXN | F_U>(P, a, s) : launch_fused<F_MAXN>(P, a, s);  // max-norm rules: x every iteration
+      else rc = (k & 1) ? launch_fused<F_X2>(P, a, s) : launch_fused<F_NOX>(P, a, s);
       ++kernels;
       if (k == k0) EV(P->ev[2], s, cudaEventRecordExternal);
       if (k == k0 + 1) EV(P->ev[9], s, cudaEventRecordExternal);
@@ -232,7 +233,7 @@ struct SolveCall {
   void* user;
   const volatile int* stop_flag;
   bool csr, with_u, report;
-  bool xdefer = false, fused = false, use_cluster = false, interrupted = false;
+  bool xdefer = false, fused = false, fused_maxn = false, use_cluster = false, interrupted = false;
   unsigned int consumed = 0;  // callback records already delivered
   double dot_ms = 0.0, upd_even_ms = 0.0, upd_odd_ms = 0.0;
   int samples = 0;
@@ -455,15 +456,17 @@ static int run_graph_solve(SolveCall& c) {
   b200cg_plan_s* P = c.P;
   const b200cg_params* prm = c.prm;
   cudaStream_t s = P->stream;
-  // single-sweep iteration (the default): relative-residual rule without report; sharded plans need the peer-memory
-  // exchange and at least 4 rows per rank (every rank sees all cuts, so all ranks decide alike)
+  // single-sweep iteration (the default): relative-residual rule without report - sharded plans need the peer-memory
+  // exchange and at least 4 rows per rank (every rank sees all cuts, so all ranks decide alike) - and MSGSolver's max-norm
+  // rules on a single-GPU plan (sharded plans run them as dot sweep + update sweep)
   const bool want_fused = prm->single_sweep == 1 || (prm->single_sweep == 0 && P->single_sweep_default);
   bool fused_ok = P->desc.world <= 1;
-  if (!fused_ok && P->peer_mode) {
+  if (!fused_ok && P->peer_mode && prm->rule == B200CG_RULE_REL_L2) {
     fused_ok = true;
     for (int r = 0; r < P->desc.world; ++r) fused_ok = fused_ok && (P->ycuts[r + 1] - P->ycuts[r] >= 4);
   }
-  c.fused = want_fused && fused_ok && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2;
+  c.fused = want_fused && fused_ok && !c.csr && !c.report;
+  c.fused_maxn = c.fused && prm->rule == B200CG_RULE_MAXNORM;
   RET(launch_init(c));
   int K = prm->iters_per_graph > 0 ? prm->iters_per_graph : default_iters_per_graph(P);
   if (prm->max_it > 0) K = std::min(K, prm->max_it + 1);
@@ -472,9 +475,10 @@ static int run_graph_solve(SolveCall& c) {
   // iteration plus the init record
   K = std::min(K, c.report ? CB_LOG_CAP / 2 : (c.cb ? CB_LOG_CAP - 2 : CB_LOG_CAP));
   // x-deferral: the relative-residual rule never looks at x, so x is only touched every other iteration
-  c.xdefer = c.fused || (P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2);
-  const int variant = c.fused ? V_FUSED
-                              : (c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0)));
+  c.xdefer = (c.fused && !c.fused_maxn) || (P->x_deferral && !c.csr && !c.report && prm->rule == B200CG_RULE_REL_L2);
+  const int variant = c.fused_maxn ? (V_FUSED | V_MAXN | (c.with_u ? V_U : 0))
+                      : c.fused    ? V_FUSED
+                                   : (c.xdefer ? V_XDEFER : ((c.with_u ? V_U : 0) | (c.report ? V_REPORT : 0) | (c.csr ? V_CSR : 0)));
   // two cached graphs per (variant, K): with event nodes (first launch of a solve: kernel times) and without
   GraphEntry& g_timed = P->graphs[(variant | V_TIMED) * 4096 + K];
   GraphEntry& g_plain = P->graphs[variant * 4096 + K];

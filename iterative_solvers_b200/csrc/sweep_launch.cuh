@@ -102,16 +102,19 @@ static int launch_fused_cfg(b200cg_plan_s* P, TileArgs a, cudaStream_t s) {
 // 1.5 %, these two on top (profiles/r2_single_sweep.md) - the ring is deep enough, so the alternatives are gone.
 template <int FLAGS>
 static int launch_fused_flags(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (P->fused_cw == 14) {  // experiment: one wide CTA per SM
-    if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2, 14>(P, a, s);
+  constexpr bool with_x = (FLAGS & (F_X2 | F_MAXN)) != 0;  // three (four with u) streams: two stages
+  if (P->fused_cw == 14) {  // slabs of >= 4 M unknowns: one wide CTA per SM
+    if constexpr (with_x) return launch_fused_cfg<FLAGS, 4, 2, 14>(P, a, s);
     else return launch_fused_cfg<FLAGS, 4, 4, 14>(P, a, s);
   }
-  if constexpr ((FLAGS & F_X2) != 0) return launch_fused_cfg<FLAGS, 4, 2, FUSED_CW>(P, a, s);
+  if constexpr (with_x) return launch_fused_cfg<FLAGS, 4, 2, FUSED_CW>(P, a, s);
   else return launch_fused_cfg<FLAGS, 4, 3, FUSED_CW>(P, a, s);
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if (a.defer == 2) return launch_fused_flags<FLAGS | F_SHARD>(P, a, s);  // sharded plan, peer memory
+  if constexpr ((FLAGS & F_MAXN) == 0) {  // (the max-norm flavour serves single-GPU plans)
+    if (a.defer == 2) return launch_fused_flags<FLAGS | F_SHARD>(P, a, s);  // sharded plan, peer memory
+  }
   return launch_fused_flags<FLAGS>(P, a, s);
 }
 

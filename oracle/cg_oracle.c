@@ -275,6 +275,86 @@ void cgo_mf_solve_single(const cgo_grid* g, const double* b, double eps, int max
   info->seconds = now_s() - t0;
 }
 
+/* NOT a reference function: MSGSolver::solve (msg_solver.cpp:10-212) on the matrix-free operator with alpha from the
+ * single-reduction recurrence - r.z is replaced by gamma = r.r of the same residual (equal in exact arithmetic: z - r is a
+ * multiple of the previous direction, to which r is orthogonal) and Az.z by delta - beta gamma / alpha_prev - everything
+ * else (update order, the three max-norm rules and their order, beta = (|r'|_2)^2 / r.z, callback cadence) as in
+ * cgo_msg_solve. The CPU statement of what the product's single sweep computes under the max-norm rules
+ * (csrc/fused_kernel.cuh, F_MAXN); tests compare it with cgo_msg_solve. */
+void cgo_msg_solve_single(const cgo_grid* g, const double* b, const double* u, double eps_p, double eps_r, double eps_e,
+                          int max_it, double* x, cgo_msg_info* info, double* cb_log, int cb_cap) {
+  long n = cgo_size(g);
+  double t0 = now_s();
+  double* r = (double*)malloc(sizeof(double) * n);
+  double* z = (double*)malloc(sizeof(double) * n);
+  double* A_z = (double*)malloc(sizeof(double) * n);
+  double* A_r = (double*)malloc(sizeof(double) * n);
+  int ncb = 0;
+  for (long i = 0; i < n; ++i) { x[i] = 0.0; r[i] = b[i]; z[i] = 0.0; }
+  double gamma = dot(n, r, r);
+  double r_norm = sqrt(gamma);
+  double r_max_norm = max_norm(n, r);
+  int iterationsDone = 0, converged = 0, stop_reason = CGO_STOP_ITERATIONS;
+  double precision_max_norm = DBL_MAX, error_max_norm = DBL_MAX;
+  if (u) {
+    double mx = 0.0;
+    for (long i = 0; i < n; ++i) { double t = fabs(x[i] - u[i]); if (t > mx) mx = t; }
+    error_max_norm = mx;
+  }
+#define CGO_CB1(it)                                                                  \
+  do {                                                                               \
+    if (cb_log && ncb < cb_cap) {                                                    \
+      cb_log[4 * ncb + 0] = (double)(it); cb_log[4 * ncb + 1] = precision_max_norm;  \
+      cb_log[4 * ncb + 2] = r_max_norm;   cb_log[4 * ncb + 3] = error_max_norm;      \
+    }                                                                                \
+    ++ncb;                                                                           \
+  } while (0)
+  CGO_CB1(0);
+  cgo_apply(g, r, A_r);
+  double rz = gamma;                       /* r.z with z = r */
+  double alpha = rz / dot(n, r, A_r);      /* first step: z = r, so Az.z = r.Ar */
+  double beta = 0.0;
+  while (iterationsDone < max_it) {
+    for (long i = 0; i < n; ++i) z[i] = r[i] + beta * z[i];
+    cgo_apply(g, z, A_z);
+    double dmax = 0.0, emax = 0.0;
+    for (long i = 0; i < n; ++i) {
+      double xn = x[i] + alpha * z[i];
+      double d = fabs(xn - x[i]);
+      if (d > dmax) dmax = d;
+      x[i] = xn;
+      if (u) { double e = fabs(xn - u[i]); if (e > emax) emax = e; }
+    }
+    for (long i = 0; i < n; ++i) r[i] = r[i] - alpha * A_z[i];
+    iterationsDone++;
+    cgo_apply(g, r, A_r);
+    double gamma_new = dot(n, r, r), delta = dot(n, r, A_r);
+    r_norm = sqrt(gamma_new);
+    r_max_norm = max_norm(n, r);
+    precision_max_norm = dmax;
+    if (u) error_max_norm = emax;
+    if (eps_p > 0 && precision_max_norm < eps_p) { converged = 1; stop_reason = CGO_STOP_PRECISION; break; }
+    if (eps_r > 0 && r_max_norm < eps_r) { converged = 1; stop_reason = CGO_STOP_RESIDUAL; break; }
+    if (eps_e > 0 && u && error_max_norm < eps_e) { converged = 1; stop_reason = CGO_STOP_EXACT_ERROR; break; }
+    beta = (r_norm * r_norm) / rz;
+    alpha = gamma_new / (delta - beta * gamma_new / alpha);
+    rz = gamma_new;
+    if (iterationsDone % 100 == 0 || iterationsDone == 1) CGO_CB1(iterationsDone);
+  }
+  CGO_CB1(iterationsDone);
+#undef CGO_CB1
+  info->iterations = iterationsDone;
+  info->converged = converged;
+  info->stop_reason = stop_reason;
+  info->r_max = r_max_norm;
+  info->dx_max = precision_max_norm;
+  info->err_max = error_max_norm;
+  info->r_l2 = r_norm;
+  info->n_callbacks = ncb;
+  free(r); free(z); free(A_z); free(A_r);
+  info->seconds = now_s() - t0;
+}
+
 /* Neighbour list of an unknown in the reference's per-row order; returns the count (grid_system.cpp:192-218). */
 static int row_entries(const cgo_grid* g, long row, int* cols, double* vals) {
   int xi, yi, k = 0;

@@ -88,6 +88,9 @@ typedef struct {
 void cgo_msg_solve(long nrows, const int* row_map, const int* entries, const double* values, const double* b,
                    const double* u, double eps_p, double eps_r, double eps_e, int max_it, double* x,
                    cgo_msg_info* info, double* cb_log, int cb_cap);
+/* not a reference function: the same rules with alpha from the single-reduction recurrence, matrix-free operator */
+void cgo_msg_solve_single(const cgo_grid* g, const double* b, const double* u, double eps_p, double eps_r, double eps_e,
+                          int max_it, double* x, cgo_msg_info* info, double* cb_log, int cb_cap);
 
 #ifdef __cplusplus
 }

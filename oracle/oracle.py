@@ -161,7 +161,15 @@ class Oracle:
         return y
 
     def msg_solve(self, csr=None, b=None, u=None, eps_p=1e-6, eps_r=1e-6, eps_e=-1.0, max_it=10000,
-                  cb_cap=0):
+                  cb_cap=0, accurate_dots=False):
+        """accurate_dots=True: diagnostic long-double summation instead of the reference's sequential fp64."""
+        self.L.cgo_set_dot_mode(1 if accurate_dots else 0)
+        try:
+            return self._msg_solve(csr, b, u, eps_p, eps_r, eps_e, max_it, cb_cap)
+        finally:
+            self.L.cgo_set_dot_mode(0)
+
+    def _msg_solve(self, csr, b, u, eps_p, eps_r, eps_e, max_it, cb_cap):
         row_map, entries, values = self.csr() if csr is None else csr
         b = self.rhs() if b is None else np.ascontiguousarray(b, dtype=np.float64)
         nrows = len(row_map) - 1
@@ -171,6 +179,22 @@ class Oracle:
         self.L.cgo_msg_solve(C.c_long(nrows), _opt(row_map), _opt(entries), _opt(values), _opt(b), _opt(u),
                              C.c_double(eps_p), C.c_double(eps_r), C.c_double(eps_e), int(max_it), _opt(x),
                              C.byref(info), _opt(log), int(cb_cap))
+        out = dict(x=x, iterations=info.iterations, converged=bool(info.converged),
+                   stop_reason=STOP_NAMES[info.stop_reason], r_max=info.r_max, dx_max=info.dx_max,
+                   err_max=info.err_max, r_l2=info.r_l2, seconds=info.seconds, n_callbacks=info.n_callbacks)
+        if cb_cap:
+            out["callbacks"] = log[: min(cb_cap, info.n_callbacks)]
+        return out
+
+    def msg_solve_single(self, b=None, u=None, eps_p=1e-6, eps_r=1e-6, eps_e=-1.0, max_it=10000, cb_cap=0):
+        """MSGSolver's rules with alpha from the single-reduction recurrence on the matrix-free operator (not a reference
+        function; see cg_oracle.c)."""
+        b = self.rhs() if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.N)
+        info = MsgInfo()
+        log = np.zeros((cb_cap, 4)) if cb_cap else None
+        self.L.cgo_msg_solve_single(C.byref(self.g), _opt(b), _opt(u), C.c_double(eps_p), C.c_double(eps_r),
+                                    C.c_double(eps_e), int(max_it), _opt(x), C.byref(info), _opt(log), int(cb_cap))
         out = dict(x=x, iterations=info.iterations, converged=bool(info.converged),
                    stop_reason=STOP_NAMES[info.stop_reason], r_max=info.r_max, dx_max=info.dx_max,
                    err_max=info.err_max, r_l2=info.r_l2, seconds=info.seconds, n_callbacks=info.n_callbacks)

@@ -38,3 +38,43 @@ def test_c_oracle_single_reduction_variant(oracle_mod, n, a_tag, iters):
     assert one["converged"]
     assert np.max(np.abs(one["x"] - ref["x"])) <= 1e-12 * np.max(np.abs(ref["x"]))
     assert abs(one["r_norm"] - ref["r_norm"]) <= 1e-6 * ref["r_norm"]
+
+
+@pytest.mark.parametrize("n,a_tag", [(6, 1), (30, 1), (128, 0)])
+def test_c_oracle_single_reduction_variant_of_the_maxnorm_rules(oracle_mod, golden_ref, n, a_tag):
+    """MSGSolver's rules with alpha from the recurrence (cgo_msg_solve_single - what the product's single sweep computes
+    under the max-norm rules) against the fixtures the unmodified reference produced: the pinned 14 / 79 / 102 / 355 / 482
+    iterations, the same stop reasons, x and the reported norms at rounding distance, the same callback cadence."""
+    a, b = {0: (0.0, 1.0), 1: (1.0, 2.0)}[a_tag]
+    tag = f"grid_n{n}_a{a_tag}"
+    eps = 1e-6 if n <= 30 else 1e-8
+    o = oracle_mod.Oracle(n, n, a, b, a, b)
+    rhs, u = golden_ref[tag + "_rhs"], golden_ref[tag + "_true"]
+    for cname, kw in {"pr": dict(eps_p=eps, eps_r=eps), "r": dict(eps_p=-1.0, eps_r=eps)}.items():
+        info_ref = golden_ref[f"{tag}_msg_{cname}_info"]  # iterations, converged, stop reason, r_max, dx_max, err_max
+        cb_ref = golden_ref[f"{tag}_msg_{cname}_cb"]
+        one = o.msg_solve_single(b=rhs, u=u, max_it=10000, cb_cap=64, **kw)
+        assert one["iterations"] == int(info_ref[0]) and one["converged"] == bool(info_ref[1])
+        assert one["stop_reason"] == oracle_mod.STOP_NAMES[int(info_ref[2])]
+        assert np.max(np.abs(one["x"] - golden_ref[f"{tag}_msg_{cname}_x"])) <= 1e-12 * np.max(np.abs(u))
+        assert abs(one["dx_max"] - info_ref[4]) <= 1e-6 * info_ref[4]
+        assert abs(one["err_max"] - info_ref[5]) <= 1e-9 * info_ref[5]
+        assert abs(one["r_max"] - info_ref[3]) <= 1e-3 * info_ref[3] + 1e-12 * np.max(np.abs(rhs))
+        assert np.array_equal(one["callbacks"][:, 0], cb_ref[:, 0])
+        assert np.allclose(one["callbacks"][1:, 1:], cb_ref[1:, 1:], rtol=1e-3, atol=0)
+
+
+@pytest.mark.parametrize("n,with_u", [(64, True), (200, True), (256, False)])
+def test_maxnorm_single_reduction_vs_reference_order_on_larger_grids(oracle_mod, n, with_u):
+    """Beyond the fixtures: cgo_msg_solve (the reference's arithmetic on the assembled matrix) and the single-reduction variant
+    stop at the same iteration for the same reason, also under the exact-error rule."""
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0)
+    u = o.true_solution() if with_u else None
+    rules = [dict(eps_p=1e-8, eps_r=1e-8), dict(eps_p=-1.0, eps_r=1e-7)]
+    if with_u:
+        rules.append(dict(eps_p=-1.0, eps_r=-1.0, eps_e=2e-4 if n == 64 else 2e-5))
+    for kw in rules:
+        ref = o.msg_solve(u=u, max_it=20000, **kw)
+        one = o.msg_solve_single(u=u, max_it=20000, **kw)
+        assert one["iterations"] == ref["iterations"] and one["stop_reason"] == ref["stop_reason"], (kw, ref["iterations"])
+        assert np.max(np.abs(one["x"] - ref["x"])) <= 1e-12 * np.max(np.abs(ref["x"]))
