@@ -86,10 +86,12 @@ class Slab:
 
 
 def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, slab=None, nb_below=None,
-          nb_above=None, warps=WARPS):
+          nb_above=None, warps=WARPS, maxn=False, u=None):
     """One launch of the kernel over all tiles; returns (gamma', delta'). slab / nb_*: the F_SHARD variant - this
     rank's Slab and the (r_out, p_out) arrays of the neighbour ranks, whose halo rows receive this slab's two first /
-    last rows."""
+    last rows. maxn: the F_MAXN flavour (MSGSolver's rules) - x += alpha * p every iteration and the maxima |r'|_inf,
+    |x' - x|_inf, |x' - u|_inf (u: pitched true solution or None) come back as a third value; FULL stages read x and u
+    unmasked too, so the maxima are taken under selects."""
     shard = nb_below is not None or nb_above is not None or slab is not None
     if slab is None:
         slab = Slab(G, 1, G.m, False, False)  # one rank owning every row: rows 0 .. m stored, no extra rows in use
@@ -99,6 +101,7 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
     writer = (lane >= 1) & (lane <= 30) & (warp >= 0)
     strip_cols = WARP_STEP * warps + 4
     gam = dlt = 0.0
+    mx = [0.0, 0.0, 0.0]  # |r'|_inf, |dx|_inf, |x' - u|_inf
 
     def stencil(c, l, r, t, b):
         v = G.A * c
@@ -115,6 +118,7 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
         P1x, P1y, P2x, P2y, LP1, RP1 = z, z, z, z, z, z
         R1x, R1y, R2x, R2y, LR1, RR1 = z, z, z, z, z, z
         r1x, r1y, x1x, x1y, q1x, q1y = z, z, z, z, z, z
+        u1x, u1y = z, z
         k1a = k1b = np.zeros((warps, 32), dtype=bool)
         for y in range(ya - 2, yb + 2):
             # the stage this row arrives in (HS rows from ya-2 on) and whether the kernel takes its FULL path there
@@ -133,17 +137,23 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
                     return buf
                 sp, sr = stage(p_in), stage(r_in)
                 cpx, cpy, crx, cry = sp[sc], sp[sc + 1], sr[sc], sr[sc + 1]
-                if x2 and ya <= y < yb:
+                if (x2 or maxn) and ya <= y < yb:
                     sx = stage(x)
                     cxx, cxy = sx[sc], sx[sc + 1]
                 else:
                     cxx = cxy = z
+                if maxn and u is not None and ya <= y < yb:
+                    su = stage(u)
+                    cux, cuy = su[sc], su[sc + 1]
+                else:
+                    cux = cuy = z
             else:
-                cpx = cpy = crx = cry = cxx = cxy = z
+                cpx = cpy = crx = cry = cxx = cxy = cux = cuy = z
             if not full:  # FULL stages read their inputs unmasked (zeros outside the unknowns, stale data only where masked later)
                 cpx, cpy = np.where(k0a, cpx, 0.0), np.where(k0b, cpy, 0.0)
                 crx, cry = np.where(k0a, crx, 0.0), np.where(k0b, cry, 0.0)
                 cxx, cxy = np.where(k0a, cxx, 0.0), np.where(k0b, cxy, 0.0)
+                cux, cuy = np.where(k0a, cux, 0.0), np.where(k0b, cuy, 0.0)
             P0x, P0y = crx + beta * cpx, cry + beta * cpy
             LP0, RP0 = shfl_up(P0y), shfl_down(P0x)
             ap0 = stencil(P1x, LP1, P1y, P0x, P2x)
@@ -172,6 +182,21 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
                     x[yy, cols + 1] = ((x1y + alpha_prev * q1y) + alpha * P1y)[st]
                 w = writer & np.ones((warps, 32), dtype=bool)
                 gam += float(np.sum(R0x[w] * R0x[w]) + np.sum(R0y[w] * R0y[w]))
+                if maxn:
+                    with np.errstate(invalid="ignore"):
+                        xmx, xmy = x1x + alpha * P1x, x1y + alpha * P1y
+                        x[yy, cols], x[yy, cols + 1] = xmx[st], xmy[st]
+                        # the kernel's selects: writer lanes, unknown columns (generic rows: k1a / k1b; FULL rows: ma / mb,
+                        # the same sets there); np.max would hand a NaN from a stale column through
+                        d0 = np.where(writer & k1a, np.abs(xmx - x1x), 0.0)
+                        d1 = np.where(writer & k1b, np.abs(xmy - x1y), 0.0)
+                        mx[0] = max(mx[0], float(np.max(np.abs(R0x[w]))), float(np.max(np.abs(R0y[w]))))
+                        mx[1] = max(mx[1], float(np.max(d0)), float(np.max(d1)))
+                        if u is not None:
+                            e0 = np.where(writer & k1a, np.abs(xmx - u1x), 0.0)
+                            e1 = np.where(writer & k1b, np.abs(xmy - u1y), 0.0)
+                            mx[2] = max(mx[2], float(np.max(e0)), float(np.max(e1)))
+                    assert np.all(np.isfinite(mx))
             LR0, RR0 = shfl_up(R0y), shfl_down(R0x)
             w = writer & np.ones((warps, 32), dtype=bool)
             if ya <= y - 2 < yb:
@@ -181,8 +206,57 @@ def sweep(G, tiles, r_in, p_in, x, r_out, p_out, alpha, beta, alpha_prev, x2, sl
             P2x, P2y, P1x, P1y, LP1, RP1 = P1x, P1y, P0x, P0y, LP0, RP0
             R2x, R2y, R1x, R1y, LR1, RR1 = R1x, R1y, R0x, R0y, LR0, RR0
             r1x, r1y, x1x, x1y, q1x, q1y = crx, cry, cxx, cxy, cpx, cpy
+            u1x, u1y = cux, cuy
             k1a, k1b = k0a, k0b
+    if maxn:
+        return gam, dlt, mx
     return gam, dlt
+
+
+def run_maxn(n, m, lshape, iters, tile_rows=0, sms=4, warps=WARPS, with_u=True):
+    """The F_MAXN flavour (MSGSolver's rules in one sweep): x every iteration and the three maxima, against a plain numpy
+    statement of the same recurrence on the node grid (oracle/cg_oracle.c: cgo_msg_solve_single)."""
+    G = Grid(n, m, lshape)
+    domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
+    tiles, _ = capi.work_split(m, n, domain=domain, sms=sms, ctas_per_sm=2 if warps == 7 else 1, tile_rows=tile_rows,
+                               fused=2 if warps == 14 else 1)
+    rng = np.random.default_rng(n * 1000 + m + 7)
+    b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+    ut = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+
+    r = b.copy(); z = np.zeros_like(b); xs = np.zeros_like(b)
+    gamma = float(np.sum(r * r)); alpha = gamma / float(np.sum(r * G.apply(r))); beta = 0.0; rz = gamma
+    hist = []
+    for _ in range(iters):
+        z = r + beta * z
+        xn = xs + alpha * z
+        dmax = float(np.max(np.abs(xn - xs))); xs = xn
+        r = r - alpha * G.apply(z)
+        g2 = float(np.sum(r * r)); d2 = float(np.sum(r * G.apply(r)))
+        hist.append((g2, d2, float(np.max(np.abs(r))), dmax, float(np.max(np.abs(xs - ut)))))
+        beta = (np.sqrt(g2) * np.sqrt(g2)) / rz
+        alpha = g2 / (d2 - beta * g2 / alpha)
+        rz = g2
+
+    rb = [G.to_pitched(b), np.zeros((G.yrows, G.pitch))]
+    pb = [np.zeros((G.yrows, G.pitch)), np.zeros((G.yrows, G.pitch))]
+    x = np.zeros((G.yrows, G.pitch))
+    up = G.to_pitched(ut) if with_u else None
+    gamma = float(np.sum(b * b)); alpha = gamma / float(np.sum(b * G.apply(b))); beta = 0.0; rz = gamma
+    worst = 0.0
+    for k in range(iters):
+        par = k & 1
+        g2, d2, mx = sweep(G, tiles, rb[par], pb[par], x, rb[par ^ 1], pb[par ^ 1], alpha, beta, 0.0, x2=False,
+                           warps=warps, maxn=True, u=up)
+        ref = hist[k]
+        worst = max(worst, abs(g2 - ref[0]) / ref[0], abs(d2 - ref[1]) / abs(ref[1]), abs(mx[0] - ref[2]) / ref[2],
+                    abs(mx[1] - ref[3]) / ref[3], abs(mx[2] - ref[4]) / ref[4] if with_u else 0.0)
+        beta = (np.sqrt(g2) * np.sqrt(g2)) / rz
+        alpha = g2 / (d2 - beta * g2 / alpha)
+        rz = g2
+    xr = G.from_pitched(x)
+    assert np.all(np.isfinite(xr)) and not np.any(xr[~G.mask])
+    return worst, np.max(np.abs(xr - xs)) / np.max(np.abs(xs)), len(tiles)
 
 
 def run(n, m, lshape, iters, tile_rows=0, sms=4, warps=WARPS):
@@ -311,4 +385,12 @@ if __name__ == "__main__":
         worst, dx, dr = run_sharded(n, m, lshape, iters, world, tile_rows=tr)
         print(f"n={n} m={m} {'L' if lshape else 'rect'} {world} slabs tile_rows={tr}: dots {worst:.1e}, x {dx:.1e}, r {dr:.1e}")
         assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
+    for n, m, lshape, iters, tr, warps, with_u in [(30, 30, True, 5, 0, 7, True), (64, 64, True, 5, 5, 7, True),
+                                                   (130, 90, True, 4, 0, 7, False), (77, 33, False, 4, 3, 7, True),
+                                                   (1000, 40, True, 3, 0, 7, True), (430, 26, False, 3, 4, 7, True),
+                                                   (900, 30, True, 3, 0, 14, True), (1700, 26, False, 3, 4, 14, False)]:
+        worst, dx, nt = run_maxn(n, m, lshape, iters, tr, warps=warps, with_u=with_u)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} warps={warps} max-norm flavour"
+              f"{'' if with_u else ' (no u)'}: sums and maxima {worst:.1e}, x {dx:.1e}")
+        assert worst < 1e-12 and dx < 1e-12
     print("MODEL_OK")

@@ -50,3 +50,14 @@ def test_wide_geometry_model(model, n, m, lshape, iters, tile_rows):
     """Slabs of >= 4 M unknowns run one 15-warp CTA per SM on 840-column strips (14 consumer warps): same data flow."""
     worst, dx, dr, ntiles = model.run(n, m, lshape, iters, tile_rows, warps=14)
     assert worst < 1e-12 and dx < 1e-12 and dr < 1e-12
+
+
+@pytest.mark.parametrize("n,m,lshape,iters,tile_rows,warps,with_u", [(30, 30, True, 5, 0, 7, True), (64, 64, True, 5, 5, 7, True),
+                                                                    (130, 90, True, 4, 0, 7, False), (430, 26, False, 3, 4, 7, True),
+                                                                    (845, 64, True, 3, 0, 7, True), (900, 30, True, 3, 0, 14, True),
+                                                                    (1700, 26, False, 3, 4, 14, False)])
+def test_maxnorm_flavour_model(model, n, m, lshape, iters, tile_rows, warps, with_u):
+    """F_MAXN (MSGSolver's rules in one sweep): x every iteration, |r'|_inf, |x' - x|_inf, |x' - u|_inf under the kernel's
+    selects - FULL stages hand x and u on unmasked, so a stale (NaN) column would surface in a maximum."""
+    worst, dx, ntiles = model.run_maxn(n, m, lshape, iters, tile_rows, warps=warps, with_u=with_u)
+    assert ntiles >= 1 and worst < 1e-12 and dx < 1e-12
