@@ -111,12 +111,12 @@ typedef struct {
   int single_sweep;        /* matrix-free operator: each iteration runs as ONE sweep by forming alpha from the single-reduction CG
                               recurrence (Chronopoulos-Gear) instead of p.Ap - the same iterates in exact arithmetic, <= 4e-14
                               relative apart in fp64 on the reference's grids (tests/studies/single_reduction_cg.py), same
-                              iteration counts. RULE_REL_L2 without a callback: 40 instead of 56 bytes per unknown-iteration; on
-                              sharded plans it needs the peer-memory exchange and >= 4 rows per rank. RULE_MAXNORM (MSGSolver's
-                              rules, callbacks included) on a single-GPU plan: 48 (56 with u) instead of 64 (72) bytes, r.z
-                              replaced by r.r of the same residual. 0 = the plan's default (on unless B200CG_SINGLE_SWEEP=0),
-                              1 = on, 2 = never (dot sweep + update sweep with alpha = r.r / p.Ap resp. r.z / Az.z). Ignored
-                              where it does not apply (assembled operator, per-iteration report, MAXNORM on sharded plans) */
+                              iteration counts. RULE_REL_L2 without a callback: 40 instead of 56 bytes per unknown-iteration.
+                              RULE_MAXNORM (MSGSolver's rules, callbacks included): 48 (56 with u) instead of 64 (72) bytes, r.z
+                              replaced by r.r of the same residual. On sharded plans it needs the peer-memory exchange and >= 4
+                              rows per rank. 0 = the plan's default (on unless B200CG_SINGLE_SWEEP=0), 1 = on, 2 = never (dot
+                              sweep + update sweep with alpha = r.r / p.Ap resp. r.z / Az.z). Ignored where it does not apply
+                              (assembled operator, per-iteration report, NCCL-fallback exchange) */
   int preconditioner;      /* b200cg_preconditioner. B200CG_PRECOND_MULTIGRID (opt-in; the reference has no preconditioner,
                               solver.hpp:17-66 is the base class kept for one): CG preconditioned by a geometric-multigrid
                               V-cycle - matrix-free operator, RULE_REL_L2, no callback, single-GPU plan; the iteration

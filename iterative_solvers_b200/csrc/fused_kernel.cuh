@@ -52,7 +52,6 @@ struct FusedCfg {
   // index yrows, row yhi+1 at index yrows+1) - and the iteration's two sums cross the ranks through the PeerSync slots,
   // alternating the slot by iteration parity: ONE publish-and-wait per iteration.
   static constexpr bool SHARD = (FLAGS & F_SHARD) != 0;
-  static_assert(!(SHARD && MAXN), "the max-norm flavour of the single sweep serves single-GPU plans");
   static_assert(!(X2 && MAXN), "x-deferral and the max-norm rules exclude each other");
 };
 
@@ -484,27 +483,29 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == FUSED_CW ? 2 : 1) cg_fuse
   bool stop_req = poll_stop(st, a.stop_flag);
   double gamma = acc_s[0];
   double delta = acc_s[1];
-  if (MAXN) {
-    finalize_fused_maxnorm(st, a.cb_log, gamma, delta, acc_m[0], acc_m[MI_DX], LOAD_U ? acc_m[MI_E] : DBL_MAX);
-    apply_stop(st, stop_req);
-    return;
-  }
   if (SHARD) {
-    // this rank's two sums to every rank, everyone's back; the slot alternates with the iteration parity so that a fast
+    // this rank's two sums (and, under the max-norm rules, its maxima) to every rank, everyone's back; the slot alternates
+    // from iteration to iteration (x-deferral: with the flavour; max-norm rules: with the iteration count) so that a fast
     // rank's next publication cannot overwrite values a slow rank is still reading
-    const int phase = X2 ? 1 : 0;
-    double mine[2] = {gamma, delta}, none[1] = {0.0}, total[4];
+    const int phase = MAXN ? (st->it & 1) : (X2 ? 1 : 0);
+    double mine[2] = {gamma, delta}, total[4], mx_all[3];
     unsigned long long* tr = a.peer_trace ? a.peer_trace + 4 * (size_t)(st->it % PEER_TRACE_CAP) : nullptr;
     if (tr) tr[0] = global_ns();
-    peer_publish<2, 0>(a.peers, st, phase, mine, none, stop_req);
+    peer_publish<2, NM>(a.peers, st, phase, mine, acc_m, stop_req);
     if (tr) tr[1] = global_ns();
-    if (!peer_collect(st, a.peers, phase, total, &stop_req)) return;
+    if (!peer_collect(st, a.peers, phase, total, &stop_req, mx_all)) return;
     if (tr) tr[2] = global_ns();
     gamma = total[0];
     delta = total[1];
-    finalize_fused(st, gamma, delta, FLAGS);
+    if (MAXN) finalize_fused_maxnorm(st, a.cb_log, gamma, delta, mx_all[0], mx_all[MI_DX], LOAD_U ? mx_all[MI_E] : DBL_MAX);
+    else finalize_fused(st, gamma, delta, FLAGS);
     apply_stop(st, stop_req);
     if (tr) tr[3] = global_ns();
+    return;
+  }
+  if (MAXN) {
+    finalize_fused_maxnorm(st, a.cb_log, gamma, delta, acc_m[0], acc_m[MI_DX], LOAD_U ? acc_m[MI_E] : DBL_MAX);
+    apply_stop(st, stop_req);
     return;
   }
   finalize_fused(st, gamma, delta, FLAGS);

@@ -338,7 +338,8 @@ __device__ __forceinline__ void peer_finalize(DevState* st, CbRecord* log, const
 
 // The wait half of peer_finalize alone (single-sweep kernel): true when every rank's publication of this epoch of
 // `phase` has landed; the summed slots come back in s[0..3]. On a timeout the solve is ended with comm_error.
-__device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, int phase, double (&s)[4], bool* stop_req) {
+__device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, int phase, double (&s)[4], bool* stop_req,
+                                             double* mx = nullptr /* [3]: the maxima over the ranks of slots 4..6 */) {
   const unsigned long long epoch = st->epoch[phase] + 1ull;
   const PeerSync* mine = pl->sync[pl->rank];
   bool ok = true;
@@ -361,12 +362,19 @@ __device__ __forceinline__ bool peer_collect(DevState* st, const PeerLinks* pl, 
     return false;
   }
   s[0] = s[1] = s[2] = s[3] = 0.0;
-  double stop = 0.0;
+  double stop = 0.0, m[3] = {0.0, 0.0, 0.0};
   for (int r = 0; r < pl->world; ++r) {
     const volatile double* v = mine->vals[phase][r];
 #pragma unroll
     for (int k = 0; k < 4; ++k) s[k] += v[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m[k] = fmax(m[k], v[4 + k]);
     stop = fmax(stop, v[7]);
+  }
+  if (mx) {
+    mx[0] = m[0];
+    mx[1] = m[1];
+    mx[2] = m[2];
   }
   *stop_req = stop > 0.0;
   return true;

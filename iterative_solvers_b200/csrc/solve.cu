@@ -456,12 +456,12 @@ static int run_graph_solve(SolveCall& c) {
   b200cg_plan_s* P = c.P;
   const b200cg_params* prm = c.prm;
   cudaStream_t s = P->stream;
-  // single-sweep iteration (the default): relative-residual rule without report - sharded plans need the peer-memory
-  // exchange and at least 4 rows per rank (every rank sees all cuts, so all ranks decide alike) - and MSGSolver's max-norm
-  // rules on a single-GPU plan (sharded plans run them as dot sweep + update sweep)
+  // single-sweep iteration (the default): the relative-residual rule without report and MSGSolver's max-norm rules;
+  // sharded plans need the peer-memory exchange and at least 4 rows per rank (every rank sees all cuts, so all ranks
+  // decide alike)
   const bool want_fused = prm->single_sweep == 1 || (prm->single_sweep == 0 && P->single_sweep_default);
   bool fused_ok = P->desc.world <= 1;
-  if (!fused_ok && P->peer_mode && prm->rule == B200CG_RULE_REL_L2) {
+  if (!fused_ok && P->peer_mode) {
     fused_ok = true;
     for (int r = 0; r < P->desc.world; ++r) fused_ok = fused_ok && (P->ycuts[r + 1] - P->ycuts[r] >= 4);
   }

@@ -112,9 +112,7 @@ static int launch_fused_flags(b200cg_plan_s* P, const TileArgs& a, cudaStream_t 
 }
 template <int FLAGS>
 static int launch_fused(b200cg_plan_s* P, const TileArgs& a, cudaStream_t s) {
-  if constexpr ((FLAGS & F_MAXN) == 0) {  // (the max-norm flavour serves single-GPU plans)
-    if (a.defer == 2) return launch_fused_flags<FLAGS | F_SHARD>(P, a, s);  // sharded plan, peer memory
-  }
+  if (a.defer == 2) return launch_fused_flags<FLAGS | F_SHARD>(P, a, s);  // sharded plan, peer memory
   return launch_fused_flags<FLAGS>(P, a, s);
 }
 

@@ -369,6 +369,76 @@ def run_sharded(n, m, lshape, iters, world, sms=4, tile_rows=0):
     return worst, np.max(np.abs(xr - xs)) / np.max(np.abs(xs)), np.max(np.abs(rr - r)) / np.max(np.abs(r))
 
 
+def run_sharded_maxn(n, m, lshape, iters, world, sms=4, tile_rows=0, with_u=True):
+    """F_SHARD | F_MAXN: the max-norm flavour on row slabs - every slab streams its own rows of x and u, r' and p cross the
+    slab edges as in run_sharded, the sums are added and the maxima maximised over the ranks."""
+    G = Grid(n, m, lshape)
+    domain = (capi.DOMAIN_LSHAPE if n == m and n % 2 == 0 else capi.DOMAIN_LSHAPE_ANY) if lshape else capi.DOMAIN_RECT
+    rng = np.random.default_rng(n * 1000 + m + 11)
+    b = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+    ut = np.where(G.mask, rng.standard_normal(G.mask.shape), 0.0)
+    bp, up = G.to_pitched(b), G.to_pitched(ut)
+    slabs, tiles, us = [], [], []
+    for rank in range(world):
+        ylo, yhi, _lo, _hi, _n = capi.partition(m, n, domain=domain, rank=rank, world=world)
+        assert yhi - ylo >= 4
+        sl = Slab(G, ylo, yhi, rank > 0, rank + 1 < world)
+        uu = np.zeros_like(sl.x)
+        for y in range(ylo - 2, yhi + 2):
+            ri = sl.row_index(y)
+            if ri >= 0:
+                sl.r[0][ri] = bp[y]
+                uu[ri] = up[y]
+        slabs.append(sl)
+        us.append(uu if with_u else None)
+        tiles.append(capi.work_split(m, n, domain=domain, rank=rank, world=world, sms=sms, ctas_per_sm=2,
+                                     tile_rows=tile_rows, fused=True)[0])
+
+    r = b.copy(); z = np.zeros_like(b); xs = np.zeros_like(b)
+    gamma = float(np.sum(r * r)); alpha = gamma / float(np.sum(r * G.apply(r))); beta = 0.0; rz = gamma
+    hist = []
+    for _ in range(iters):
+        z = r + beta * z
+        xn = xs + alpha * z
+        dmax = float(np.max(np.abs(xn - xs))); xs = xn
+        r = r - alpha * G.apply(z)
+        g2 = float(np.sum(r * r)); d2 = float(np.sum(r * G.apply(r)))
+        hist.append((g2, d2, float(np.max(np.abs(r))), dmax, float(np.max(np.abs(xs - ut)))))
+        beta = (np.sqrt(g2) * np.sqrt(g2)) / rz
+        alpha = g2 / (d2 - beta * g2 / alpha)
+        rz = g2
+
+    gamma = float(np.sum(b * b)); alpha = gamma / float(np.sum(b * G.apply(b))); beta = 0.0; rz = gamma
+    worst = 0.0
+    for k in range(iters):
+        par = k & 1
+        g2 = d2 = 0.0
+        mx = [0.0, 0.0, 0.0]
+        for rank, sl in enumerate(slabs):
+            below = slabs[rank - 1] if rank > 0 else None
+            above = slabs[rank + 1] if rank + 1 < world else None
+            gg, dd, mm = sweep(G, tiles[rank], sl.r[par], sl.p[par], sl.x, sl.r[par ^ 1], sl.p[par ^ 1], alpha, beta, 0.0,
+                               x2=False, slab=sl,
+                               nb_below=((below.r[par ^ 1], below.p[par ^ 1]), below.yrows) if below else None,
+                               nb_above=((above.r[par ^ 1], above.p[par ^ 1]), above.yrows) if above else None,
+                               maxn=True, u=us[rank])
+            g2 += gg
+            d2 += dd
+            mx = [max(a, c) for a, c in zip(mx, mm)]
+        ref = hist[k]
+        worst = max(worst, abs(g2 - ref[0]) / ref[0], abs(d2 - ref[1]) / abs(ref[1]), abs(mx[0] - ref[2]) / ref[2],
+                    abs(mx[1] - ref[3]) / ref[3], abs(mx[2] - ref[4]) / ref[4] if with_u else 0.0)
+        beta = (np.sqrt(g2) * np.sqrt(g2)) / rz
+        alpha = g2 / (d2 - beta * g2 / alpha)
+        rz = g2
+    xg = np.zeros((m + 1, G.pitch))
+    for sl in slabs:
+        xg[sl.ylo:sl.yhi] = sl.x[1:1 + sl.yhi - sl.ylo]
+    xr = G.from_pitched(xg)
+    assert np.all(np.isfinite(xr)) and not np.any(xr[~G.mask])
+    return worst, np.max(np.abs(xr - xs)) / np.max(np.abs(xs))
+
+
 if __name__ == "__main__":
     for n, m, lshape, iters, tr in [(30, 30, True, 7, 0), (64, 64, True, 6, 0), (64, 64, True, 5, 5), (130, 90, True, 6, 0),
                                     (77, 33, False, 6, 3), (1000, 40, True, 4, 0), (970, 24, False, 3, 7),
@@ -391,6 +461,13 @@ if __name__ == "__main__":
                                                    (900, 30, True, 3, 0, 14, True), (1700, 26, False, 3, 4, 14, False)]:
         worst, dx, nt = run_maxn(n, m, lshape, iters, tr, warps=warps, with_u=with_u)
         print(f"n={n} m={m} {'L' if lshape else 'rect'} tile_rows={tr} tiles={nt} warps={warps} max-norm flavour"
+              f"{'' if with_u else ' (no u)'}: sums and maxima {worst:.1e}, x {dx:.1e}")
+        assert worst < 1e-12 and dx < 1e-12
+    for n, m, lshape, iters, world, tr, with_u in [(64, 64, True, 5, 2, 0, True), (130, 90, True, 4, 4, 0, True),
+                                                   (77, 60, False, 4, 3, 5, False), (1000, 40, True, 3, 2, 0, True),
+                                                   (96, 96, True, 5, 8, 0, True)]:
+        worst, dx = run_sharded_maxn(n, m, lshape, iters, world, tile_rows=tr, with_u=with_u)
+        print(f"n={n} m={m} {'L' if lshape else 'rect'} {world} slabs tile_rows={tr} max-norm flavour"
               f"{'' if with_u else ' (no u)'}: sums and maxima {worst:.1e}, x {dx:.1e}")
         assert worst < 1e-12 and dx < 1e-12
     print("MODEL_OK")

@@ -18,12 +18,15 @@ from oracle.oracle import Oracle  # noqa: E402
 FULL_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (1100, 0, 1e-6, "mf"), (333, 1, 1e-8, "mf"),
               (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
               (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (600, 0, 1e-6, "mf-2s"), (256, 0, 1e-8, "mf-w"),
-              (1100, 0, 1e-6, "mf-w"), (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s")]
+              (1100, 0, 1e-6, "mf-w"), (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s"), (128, 0, 1e-8, "msg-2s"),
+              (128, 0, 1e-8, "msg0-2s"), (256, 0, 1e-7, "msg-w"), (500, 0, 1e-5, "msg"), (333, 1, 1e-7, "msg0"),
+              (256, 0, 1e-8, "stop-msg")]
 # bench.py runs these in-process before its timed loop at N > 1 (the oracle solves take ~20 s of rank 0's host time)
 BENCH_CASES = [(64, 0, 1e-8, "mf"), (256, 0, 1e-8, "mf"), (500, 0, 1e-5, "mf"), (333, 1, 1e-8, "mf"),
                (256, 0, 1e-8, "mf-hs2"), (128, 0, 1e-8, "msg"), (128, 0, 1e-8, "msg0"), (128, 0, 1e-8, "cb"),
                (256, 0, 1e-8, "mf-2s"), (333, 1, 1e-8, "mf-2s"), (256, 0, 1e-8, "mf-w"), (500, 0, 1e-5, "mf-w"),
-               (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s")]
+               (256, 0, 1e-8, "stop"), (256, 0, 1e-8, "stop-2s"), (128, 0, 1e-8, "msg-2s"), (256, 0, 1e-7, "msg-w"),
+               (500, 0, 1e-5, "msg"), (256, 0, 1e-8, "stop-msg")]
 
 
 def run_cases(rank, world, local, cases, log=print):
@@ -31,8 +34,11 @@ def run_cases(rank, world, local, cases, log=print):
     two halo rows per side over peer memory, one publish-and-wait per iteration), "mf-2s" = the two-sweep iteration,
     "mf-hs2" = two sweeps with 2-row stages (the launch shapes are read when the plan is created), "mf-w" = the single
     sweep in the wide geometry of large slabs (840-column strips, one CTA per SM) forced onto a small grid, "stop" /
-    "stop-2s" = an interrupt raised on rank 0 ONLY must end the solve on every rank at the same iteration, "msg" / "msg0" = the
-    max-norm rules with / without a true solution, "cb" = the per-iteration report callback.
+    "stop-2s" / "stop-msg" = an interrupt raised on rank 0 ONLY must end the solve on every rank at the same iteration (single
+    sweep, two sweeps, single sweep under the max-norm rules), "msg" / "msg0" = the max-norm rules with / without a true
+    solution (single sweep on peer-memory plans: sums AND maxima cross the ranks in one publish-and-wait; the callback
+    records are compared with the oracle's), "msg-2s" / "msg0-2s" = the same as dot sweep + update sweep, "msg-w" = in the wide
+    geometry, "cb" = the per-iteration report callback.
     Returns {"cases", "ok", "max_rel", "iterations_equal", "failed"} (meaningful on rank 0)."""
 
     def fresh_comm_id():  # an NCCL unique id bootstraps exactly one communicator: one per plan
@@ -49,7 +55,7 @@ def run_cases(rank, world, local, cases, log=print):
         b, u = o.rhs(), o.true_solution()
         if kind == "mf-hs2":
             os.environ.update(hs2)
-        if kind == "mf-w":
+        if kind in ("mf-w", "msg-w"):
             os.environ["B200CG_FUSED_CW"] = "14"
         plan = capi.Plan(n, n, 0.0, 1.0, 0.0, 1.0, domain=domain, device=local, rank=rank, world=world,
                          comm_id=fresh_comm_id())
@@ -65,14 +71,15 @@ def run_cases(rank, world, local, cases, log=print):
                 refs[key] = fn()
             return refs[key]
 
-        if kind in ("stop", "stop-2s"):
+        if kind in ("stop", "stop-2s", "stop-msg"):
             # requestStop on one rank: the request travels with the per-iteration reductions (kernels poll the mapped flag
             # every 16th iteration), so all ranks report INTERRUPTED after the same 16 iterations
             import ctypes
 
             flag = ctypes.c_int(1 if rank == 0 else 0)
-            x, info = plan.solve(b=b[lo:hi], eps_rel=1e-30, max_it=100000, iters_per_graph=100, stop_flag=flag,
-                                 single_sweep=2 if kind == "stop-2s" else 0)
+            rules = dict(rule=capi.RULE_MAXNORM, eps_p=-1.0, eps_r=1e-300) if kind == "stop-msg" else dict(eps_rel=1e-30)
+            x, info = plan.solve(b=b[lo:hi], max_it=100000, iters_per_graph=100, stop_flag=flag,
+                                 single_sweep=2 if kind == "stop-2s" else 0, **rules)
             plan.close()
             seen = [None] * world
             dist.all_gather_object(seen, (info["iterations"], info["stop_reason"], info["converged"]))
@@ -95,12 +102,15 @@ def run_cases(rank, world, local, cases, log=print):
             x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], eps_rel=eps, max_it=20000,
                                  callback=lambda it, p, r, e: got_cb.append((it, p, r, e)))
             ref = reference((n, domain, eps, "cb"), lambda: o.mf_solve(b=b, eps=eps, max_it=20000, with_hist=True))
-        elif kind == "msg0":
-            x, info = plan.solve(b=b[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
-            ref = reference((n, domain, eps, "msg0"), lambda: o.msg_solve(b=b, eps_p=eps, eps_r=eps, max_it=20000))
-        else:
-            x, info = plan.solve(b=b[lo:hi], u=u[lo:hi], rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps, max_it=20000)
-            ref = reference((n, domain, eps, "msg"), lambda: o.msg_solve(b=b, u=u, eps_p=eps, eps_r=eps, max_it=20000))
+        else:  # the max-norm rules: "msg", "msg-2s", "msg-w" with the true solution, "msg0", "msg0-2s" without
+            two, with_u = kind.endswith("-2s"), not kind.startswith("msg0")
+            x, info = plan.solve(b=b[lo:hi], u=u[lo:hi] if with_u else None, rule=capi.RULE_MAXNORM, eps_p=eps, eps_r=eps,
+                                 max_it=20000, single_sweep=2 if two else 0,
+                                 callback=lambda it, p, r, e: got_cb.append((it, p, r, e)))
+            if info["single_sweep"] != (0 if two or not info["peer_exchange"] else 1):
+                failures.append((n, domain, kind, "wrong iteration scheme"))
+            ref = reference((n, domain, eps, "msg", with_u),
+                            lambda: o.msg_solve(b=b, u=u if with_u else None, eps_p=eps, eps_r=eps, max_it=20000, cb_cap=512))
         v = np.random.default_rng(n).standard_normal(o.N)
         y = plan.apply(v[lo:hi])
         res, _ = plan.postprocess(want_error=False)
@@ -117,8 +127,15 @@ def run_cases(rank, world, local, cases, log=print):
             ok = abs(info["iterations"] - ref["iterations"]) <= 1 and rel < 1e-10
             ok = ok and np.array_equal(yg, o.apply(v))
             ok = ok and np.max(np.abs(rg - (o.apply(xg) - b))) <= 1e-12 * np.max(np.abs(b))
-            if kind in ("msg", "msg0"):
+            if kind.startswith("msg"):
                 ok = ok and info["stop_reason"] == ref["stop_reason"]
+                if info["iterations"] == ref["iterations"]:  # callback cadence and values (it 0, 1, every 100, final)
+                    got, cbr = np.array(got_cb), ref["callbacks"]
+                    ok = ok and got.shape == cbr.shape and np.array_equal(got[:, 0], cbr[:, 0])
+                    ok = ok and np.allclose(got[1:, 1:3], cbr[1:, 1:3], rtol=1e-3, atol=1e-10 * np.max(np.abs(b)))
+                    ok = ok and abs(info["dx_max"] - ref["dx_max"]) <= 1e-6 * ref["dx_max"]
+                    if not kind.startswith("msg0"):
+                        ok = ok and abs(info["err_max"] - ref["err_max"]) <= 1e-9 * ref["err_max"] + 1e-10 * np.max(np.abs(u))
             if kind == "cb":
                 got = np.array(got_cb)
                 ok = ok and len(got) == len(ref["hist"]) and np.all(

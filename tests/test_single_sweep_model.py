@@ -61,3 +61,11 @@ def test_maxnorm_flavour_model(model, n, m, lshape, iters, tile_rows, warps, wit
     selects - FULL stages hand x and u on unmasked, so a stale (NaN) column would surface in a maximum."""
     worst, dx, ntiles = model.run_maxn(n, m, lshape, iters, tile_rows, warps=warps, with_u=with_u)
     assert ntiles >= 1 and worst < 1e-12 and dx < 1e-12
+
+
+@pytest.mark.parametrize("n,m,lshape,iters,world,tile_rows,with_u", [(64, 64, True, 5, 2, 0, True), (70, 60, True, 4, 3, 0, True),
+                                                                    (77, 60, False, 4, 3, 5, False), (96, 96, True, 4, 8, 0, True)])
+def test_sharded_maxnorm_flavour_model(model, n, m, lshape, iters, world, tile_rows, with_u):
+    """F_SHARD | F_MAXN: every slab streams its own rows of x and u; sums are added, maxima maximised over the ranks."""
+    worst, dx = model.run_sharded_maxn(n, m, lshape, iters, world, tile_rows=tile_rows, with_u=with_u)
+    assert worst < 1e-12 and dx < 1e-12
