@@ -11,7 +11,8 @@
 // of two rows / two columns and recomputes p and r' there. Element-wise arithmetic is unchanged (separately rounded
 // multiply/add in the reference's order, matrix_free_system.cpp:216-266, :422-438); only the way alpha is formed
 // differs, and tests/studies/single_reduction_cg.py shows the iterates stay within 4e-14 of the reference's on every
-// golden grid (same iteration counts). The default iteration of the REL_L2 rule without a report callback, on single
+// golden grid (same iteration counts). The default iteration of the REL_L2 rule without a report callback and - as the
+// F_MAXN flavour, which touches x every iteration and also reduces the three max-norms - of MSGSolver's rules, on single
 // and on sharded (peer-memory) plans; b200cg_params.single_sweep = 2 / B200CG_SINGLE_SWEEP=0 select the two-sweep one.
 //
 // Structure: the producer warp / mbarrier stage ring of stream_kernel.cuh. Consumers differ in the column mapping:

@@ -1,6 +1,7 @@
 // Shared device helpers of libb200cg: modes, kernel arguments, reductions, scalar finalisation (sm_100a, fp64).
 //
-// Two fused kernels per CG iteration (DESIGN.md "Kernels"):
+// The two-sweep scheme (stream_kernel.cuh; the single-sweep iteration of fused_kernel.cuh is the default where it applies) -
+// two fused kernels per CG iteration (DESIGN.md "Kernels"):
 //   dot phase    : p = r + beta*p_old on the fly, Ap = A p on the fly, reduces p.Ap and r.p       16 B/unknown
 //   update phase : same p / Ap recomputed, x += alpha p, r -= alpha Ap, stores x, r, p,
 //                  reduces r.r, |r|_inf, |dx|_inf (and |x-u|_inf)                                 48 B/unknown

@@ -92,8 +92,8 @@ static int build_graph(b200cg_plan_s* P, int variant, int iters, bool timed, Gra
       }
     }
     if (fused) {
-      // single-sweep iteration: one kernel; x touched on odd iterations only (the event slots of the absent dot
-      // phase collapse to zero length)
+      // single-sweep iteration: one kernel; under the REL_L2 rule x is touched on odd iterations only, under the max-norm
+      // rules every iteration (the event slots of the absent dot phase collapse to zero length)
       if (k == k0) EV(P->ev[1], s, cudaEventRecordExternal);
       if (k == k0 + 1) EV(P->ev[8], s, cudaEventRecordExternal);
       if (maxn) rc = with_u ? launch_fused<F_MAXN | F_U>(P, a, s) : launch_fused<F_MAXN>(P, a, s);  // max-norm rules: x every iteration
@@ -622,7 +622,7 @@ static void fill_info(const SolveCall& c, const DevState& st) {
   info->r_l2 = st.r_norm;
   info->r_max = st.r_max;
   info->dx_max = st.dx_max;
-  // the x-deferral / single-sweep flavours (REL_L2 without callback) do not track |x - u|_inf: nothing reads it there
+  // the x-deferral flavours (REL_L2 without callback, one or two sweeps) do not track |x - u|_inf: nothing reads it there
   info->err_max = c.xdefer ? DBL_MAX : st.err_max;
   auto span = [&](int a, int b) {
     float ms = 0.f;
