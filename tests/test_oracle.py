@@ -136,6 +136,21 @@ def test_against_live_reference(oracle_mod):
         assert rs["iterations"] == os_["iterations"] and np.array_equal(rs["x"], os_["x"])
 
 
+def test_port_equals_the_compiled_reference_at_config2_size(oracle_mod):
+    """BASELINE.json configs[1] (4096^2, 12.6 M unknowns), 5 iterations - the case tests/test_gpu_parity.py holds the GPU
+    to: the C restatement reproduces the unmodified reference's rhs and its fifth iterate bit for bit there too (same
+    operations, same sequential sums), so a comparison with the restatement IS a comparison with the reference."""
+    if not oracle_mod.Reference.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    n = 4096
+    ref = oracle_mod.Reference.MatrixFree(n, n, 0.0, 1.0, 0.0, 1.0)
+    o = oracle_mod.Oracle(n, n, 0.0, 1.0, 0.0, 1.0)
+    b = o.rhs()
+    assert ref.N == o.N == 12574721 and np.array_equal(ref.rhs(), b)
+    rs, ps = ref.solve(eps=1e-8, max_it=5), o.mf_solve(b=b, eps=1e-8, max_it=5)
+    assert rs["iterations"] == ps["iterations"] == 5 and np.array_equal(rs["x"], ps["x"])
+
+
 def test_reference_rejects_what_oracle_rejects(oracle_mod):
     """The reference numbering is only self-consistent for even n == m; the oracle refuses the rest."""
     for n, m in [(8, 6), (7, 7), (2, 2)]:
