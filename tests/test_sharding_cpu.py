@@ -101,10 +101,12 @@ def test_two_rank_slab_protocol(tmp_path, n, domain):
 
 
 # ---------------------------------------------------------------- the sharded single-sweep iteration (F_SHARD), 2 processes
-def _single_sweep_worker(rank, world, port, n, iters, out_dir):
+def _single_sweep_worker(rank, world, port, n, iters, out_dir, maxn=False):
     """Each process owns one slab of the lane-level kernel model (scripts/model_single_sweep.py) and runs the single-sweep
     iteration on it; what the CUDA kernel stores into its neighbours over NVLink travels here as gloo messages, the
-    PeerSync sums as an all-reduce. The assembled iterate must equal a global single-reduction CG."""
+    PeerSync sums as an all-reduce. The assembled iterate must equal a global single-reduction CG. maxn: the max-norm
+    flavour (MSGSolver's rules) - x every iteration, the three maxima cross the ranks as a MAX all-reduce, and every rank
+    must reach the same stop verdict at the same iteration."""
     sys.path.insert(0, ROOT)
     import importlib.util
 
@@ -154,18 +156,36 @@ def _single_sweep_worker(rank, world, port, n, iters, out_dir):
         gamma = float(np.sum(b * b))
         alpha = gamma / float(np.sum(b * G.apply(b)))
         beta = alpha_prev = 0.0
+        ut = np.where(G.mask, np.random.default_rng(n + 1).standard_normal(G.mask.shape), 0.0)
+        u_slab = np.zeros_like(sl.x)
+        for y in range(ylo - 1, yhi + 1):
+            u_slab[sl.row_index(y)] = G.to_pitched(ut)[y]
+        norms, stop_at = [], None
         for k in range(iters):
             par = k & 1
-            gg, dd = model.sweep(G, tiles, sl.r[par], sl.p[par], sl.x, sl.r[par ^ 1], sl.p[par ^ 1], alpha, beta, alpha_prev,
-                                 x2=bool(k & 1), slab=sl)
+            out = model.sweep(G, tiles, sl.r[par], sl.p[par], sl.x, sl.r[par ^ 1], sl.p[par ^ 1], alpha, beta,
+                              0.0 if maxn else alpha_prev, x2=False if maxn else bool(k & 1), slab=sl, maxn=maxn,
+                              u=u_slab if maxn else None)
             exchange(par ^ 1)
-            sums = torch.tensor([gg, dd], dtype=torch.float64)
+            sums = torch.tensor(out[:2], dtype=torch.float64)
             dist.all_reduce(sums)
             g2, d2 = float(sums[0]), float(sums[1])
-            alpha_prev = alpha if not (k & 1) else 0.0
-            beta = g2 / gamma
+            if maxn:
+                mx = torch.tensor(out[2], dtype=torch.float64)
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                norms.append([float(v) for v in mx])
+                if stop_at is None and float(mx[1]) < 0.05:  # a precision rule both ranks must trip in the same iteration
+                    stop_at = k + 1
+                beta = (np.sqrt(g2) * np.sqrt(g2)) / gamma
+            else:
+                alpha_prev = alpha if not (k & 1) else 0.0
+                beta = g2 / gamma
             alpha, gamma = g2 / (d2 - beta * g2 / alpha), g2
-        x_own = sl.x + (alpha_prev * sl.p[iters & 1] if iters & 1 else 0.0)
+        x_own = sl.x + (alpha_prev * sl.p[iters & 1] if (iters & 1 and not maxn) else 0.0)
+        if maxn:
+            seen = [None] * world
+            dist.all_gather_object(seen, (stop_at, norms))
+            assert all(v == seen[0] for v in seen)  # identical maxima, hence identical verdicts, on every rank
         parts = [None] * world
         dist.all_gather_object(parts, (ylo, yhi, x_own[1:1 + yhi - ylo]))
         if rank == 0:
@@ -183,6 +203,9 @@ def _single_sweep_worker(rank, world, port, n, iters, out_dir):
                 be = g2 / ga
                 al, ga = g2 / (d2 - be * g2 / al), g2
             assert np.max(np.abs(G.from_pitched(xg) - xs)) <= 1e-12 * np.max(np.abs(xs))
+            if maxn:  # the maxima of the last iteration against the global iterate
+                assert abs(norms[-1][0] - np.max(np.abs(r))) <= 1e-12 * np.max(np.abs(r))
+                assert abs(norms[-1][2] - np.max(np.abs(xs - ut))) <= 1e-12 * np.max(np.abs(xs - ut))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -197,4 +220,17 @@ def test_two_rank_single_sweep_protocol(tmp_path, n, iters):
     build.build_library()
     port = _free_port()
     mp.spawn(_single_sweep_worker, args=(2, port, n, iters, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+@pytest.mark.parametrize("n,iters", [(64, 5)])
+def test_two_rank_maxnorm_single_sweep_protocol(tmp_path, n, iters):
+    """F_SHARD | F_MAXN with gloo standing in for the peer-memory slots: sums added, maxima maximised, same verdict everywhere."""
+    import torch.multiprocessing as mp
+
+    from iterative_solvers_b200 import build
+
+    build.build_library()
+    port = _free_port()
+    mp.spawn(_single_sweep_worker, args=(2, port, n, iters, str(tmp_path), True), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
