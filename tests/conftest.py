@@ -28,6 +28,12 @@ def golden_ref():
 
 
 @pytest.fixture(scope="session")
+def golden_msg():
+    """More MSGSolver runs of the unmodified reference: exact-error rule, no true solution, 64 x 64, iteration cap."""
+    return np.load(os.path.join(GOLDEN, "reference_outputs_msg.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle_mod():
     from oracle import oracle
 

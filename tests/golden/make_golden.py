@@ -2,13 +2,15 @@
 
     python tests/golden/make_golden.py
 
-Two fixture files:
+Three fixture files:
 * reference_scripts.npz - the known-answer data the reference itself ships: the 16x16 matrix of
   check.py:4-19, the RHS of check_debug.py:36 and every vector/scalar of py_debug.txt:5-15, parsed
   from the files where they lie (nothing is retyped by hand).
 * reference_outputs.npz - outputs of the UNMODIFIED reference classes (oracle/_ref/libref_cg.so, built by
   oracle/Makefile from /root/reference/solver/*.cpp) on small grids: rhs, true solution, apply() on a
   seeded random vector, MatrixFreeSolver / MSGSolver / DirichletSolver solves.
+* reference_outputs_msg.npz - more MSGSolver runs of the unmodified reference: the exact-error rule (stop reason
+  EXACT_ERROR), a solve without a true solution, the 64 x 64 grid on [0,1]^2 and an iteration cap.
 The GPU box has no /root/reference; the -m gpu tests read only these fixtures.
 """
 import ast
@@ -97,9 +99,33 @@ def reference_outputs():
     return out
 
 
+STOP = ["ITERATIONS", "PRECISION", "RESIDUAL", "EXACT_ERROR", "INTERRUPTED"]
+
+
+def reference_outputs_msg():
+    """MSGSolver::solve branches the first file does not reach (msg_solver.cpp:64-72,132-139,158-162,80)."""
+    out = {}
+    cases = [("n30_a1_exact", 30, (1.0, 2.0), dict(eps_p=-1.0, eps_r=-1.0, eps_e=5e-3, max_it=10000, with_true=True)),
+             ("n30_a1_exact_first", 30, (1.0, 2.0), dict(eps_p=1e-12, eps_r=1e-12, eps_e=1e-2, max_it=10000, with_true=True)),
+             ("n30_a1_nou", 30, (1.0, 2.0), dict(eps_p=1e-7, eps_r=-1.0, eps_e=1e-3, max_it=10000, with_true=False)),
+             ("n64_a0_pr", 64, (0.0, 1.0), dict(eps_p=1e-8, eps_r=1e-8, eps_e=-1.0, max_it=10000, with_true=True)),
+             ("n64_a0_r", 64, (0.0, 1.0), dict(eps_p=-1.0, eps_r=1e-8, eps_e=-1.0, max_it=10000, with_true=True)),
+             ("n64_a0_cap", 64, (0.0, 1.0), dict(eps_p=1e-30, eps_r=1e-30, eps_e=-1.0, max_it=150, with_true=True))]
+    for tag, n, (a, b), kw in cases:
+        g = Reference.Grid(n, n, a, b, a, b)
+        s = g.msg_solve(cb_cap=256, **kw)
+        out[f"msg_{tag}_x"] = s["x"]
+        out[f"msg_{tag}_info"] = np.array([s["iterations"], int(s["converged"]), STOP.index(s["stop_reason"]), s["r_max"],
+                                           s["dx_max"], s["err_max"]])
+        out[f"msg_{tag}_cb"] = s["callbacks"]
+        out[f"msg_{tag}_params"] = np.array([n, a, b, kw["eps_p"], kw["eps_r"], kw["eps_e"], kw["max_it"], int(kw["with_true"])])
+    return out
+
+
 if __name__ == "__main__":
     build(REF)
+    np.savez_compressed(os.path.join(OUT, "reference_outputs_msg.npz"), **reference_outputs_msg())
     np.savez_compressed(os.path.join(OUT, "reference_scripts.npz"), **parse_scripts())
     np.savez_compressed(os.path.join(OUT, "reference_outputs.npz"), **reference_outputs())
-    for f in ("reference_scripts.npz", "reference_outputs.npz"):
+    for f in ("reference_scripts.npz", "reference_outputs.npz", "reference_outputs_msg.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

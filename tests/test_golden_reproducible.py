@@ -15,7 +15,8 @@ def test_fixtures_regenerate_bit_for_bit():
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
     mk.build()
-    for fresh, path in ((mk.parse_scripts(), "reference_scripts.npz"), (mk.reference_outputs(), "reference_outputs.npz")):
+    for fresh, path in ((mk.parse_scripts(), "reference_scripts.npz"), (mk.reference_outputs(), "reference_outputs.npz"),
+                        (mk.reference_outputs_msg(), "reference_outputs_msg.npz")):
         committed = np.load(os.path.join(HERE, "golden", path))
         assert set(fresh.keys()) == set(committed.files)
         for key in committed.files:

@@ -101,6 +101,32 @@ def test_assembled_path_bit_exact(oracle_mod, golden_ref, n, a_tag):
         assert np.array_equal(s["callbacks"], golden_ref[f"{tag}_msg_{cname}_cb"])
 
 
+MSG_CASES = ["n30_a1_exact", "n30_a1_exact_first", "n30_a1_nou", "n64_a0_pr", "n64_a0_r", "n64_a0_cap"]
+
+
+@pytest.mark.parametrize("tag", MSG_CASES)
+def test_msg_rules_bit_exact_on_the_extra_fixtures(oracle_mod, golden_msg, tag):
+    """MSGSolver branches beyond the first fixture file, run by the unmodified reference: the exact-error rule firing
+    (alone, and ahead of the other two), a solve without a true solution (error stays DBL_MAX, its rule is skipped), the
+    64 x 64 grid on [0,1]^2, the iteration cap (ITERATIONS, not converged). Bit for bit, callbacks included."""
+    n, a, b, eps_p, eps_r, eps_e, max_it, with_true = golden_msg[f"msg_{tag}_params"]
+    o = oracle_mod.Oracle(int(n), int(n), a, b, a, b)
+    u = o.true_solution() if with_true else None
+    s = o.msg_solve(u=u, eps_p=eps_p, eps_r=eps_r, eps_e=eps_e, max_it=int(max_it), cb_cap=256)
+    info = golden_msg[f"msg_{tag}_info"]
+    assert s["iterations"] == int(info[0]) and s["converged"] == bool(info[1])
+    assert oracle_mod.STOP_NAMES.index(s["stop_reason"]) == int(info[2])
+    assert (s["r_max"], s["dx_max"], s["err_max"]) == tuple(info[3:6])
+    assert np.array_equal(s["x"], golden_msg[f"msg_{tag}_x"])
+    assert np.array_equal(s["callbacks"], golden_msg[f"msg_{tag}_cb"])
+
+
+def test_extra_fixture_stop_reasons(golden_msg):
+    got = {tag: (int(golden_msg[f"msg_{tag}_info"][0]), int(golden_msg[f"msg_{tag}_info"][2])) for tag in MSG_CASES}
+    assert got == {"n30_a1_exact": (50, 3), "n30_a1_exact_first": (48, 3), "n30_a1_nou": (88, 1), "n64_a0_pr": (180, 1),
+                   "n64_a0_r": (238, 2), "n64_a0_cap": (150, 0)}
+
+
 def test_pinned_iteration_counts(golden_ref):
     """SURVEY 8c pins, re-derived from the unmodified reference when the fixture was made."""
     assert int(golden_ref["grid_n30_a1_msg_pr_info"][0]) == 79

@@ -78,3 +78,20 @@ def test_maxnorm_single_reduction_vs_reference_order_on_larger_grids(oracle_mod,
         one = o.msg_solve_single(u=u, max_it=20000, **kw)
         assert one["iterations"] == ref["iterations"] and one["stop_reason"] == ref["stop_reason"], (kw, ref["iterations"])
         assert np.max(np.abs(one["x"] - ref["x"])) <= 1e-12 * np.max(np.abs(ref["x"]))
+
+
+@pytest.mark.parametrize("tag", ["n30_a1_exact", "n30_a1_exact_first", "n30_a1_nou", "n64_a0_pr", "n64_a0_r", "n64_a0_cap"])
+def test_maxnorm_single_reduction_variant_on_the_extra_fixtures(oracle_mod, golden_msg, tag):
+    """The single-reduction statement of MSGSolver's rules against more runs of the unmodified reference: exact-error rule,
+    no true solution, 64 x 64, iteration cap - same iteration, same reason, x at rounding distance, same callback cadence."""
+    n, a, b, eps_p, eps_r, eps_e, max_it, with_true = golden_msg[f"msg_{tag}_params"]
+    o = oracle_mod.Oracle(int(n), int(n), a, b, a, b)
+    u = o.true_solution() if with_true else None
+    one = o.msg_solve_single(u=u, eps_p=eps_p, eps_r=eps_r, eps_e=eps_e, max_it=int(max_it), cb_cap=256)
+    info, x_ref, cb_ref = golden_msg[f"msg_{tag}_info"], golden_msg[f"msg_{tag}_x"], golden_msg[f"msg_{tag}_cb"]
+    assert one["iterations"] == int(info[0]) and one["converged"] == bool(info[1])
+    assert oracle_mod.STOP_NAMES.index(one["stop_reason"]) == int(info[2])
+    assert np.max(np.abs(one["x"] - x_ref)) <= 1e-12 * np.max(np.abs(x_ref))
+    assert abs(one["dx_max"] - info[4]) <= 1e-6 * info[4]
+    assert one["err_max"] == info[5] if not with_true else abs(one["err_max"] - info[5]) <= 1e-9 * info[5] + 1e-12
+    assert np.array_equal(one["callbacks"][:, 0], cb_ref[:, 0])
