@@ -318,28 +318,30 @@ def test_maxnorm_rules_parity(capi, golden_ref, n, a_tag, op):
                 assert np.all(np.abs(got[1:, 2] - cb_ref[1:, 2]) <= REL * bscale)
 
 
-def test_maxnorm_without_true_solution(capi, oracle_mod):
-    o = oracle_for(oracle_mod, 30, 1)
-    ref = o.msg_solve(u=None, eps_p=1e-7, eps_r=-1.0, eps_e=1e-3, max_it=10000)  # eps_e ignored without u
+def test_maxnorm_without_true_solution(capi, golden_ref, golden_msg):
+    """Against a run of the unmodified reference (tests/golden/reference_outputs_msg.npz): without a true solution the
+    error stays DBL_MAX and its rule is skipped (msg_solver.cpp:64-72,158)."""
+    info_ref, x_ref = golden_msg["msg_n30_a1_nou_info"], golden_msg["msg_n30_a1_nou_x"]
     with plan_for(capi, 30, 1) as p:
-        x, info = p.solve(b=o.rhs(), rule=capi.RULE_MAXNORM, eps_p=1e-7, eps_r=-1.0, eps_e=1e-3, max_it=10000)
-        assert info["iterations"] == ref["iterations"] and info["stop_reason"] == ref["stop_reason"]
-        assert info["err_max"] == np.finfo(np.float64).max
-        assert relmax(x, ref["x"]) < REL
+        x, info = p.solve(b=golden_ref["grid_n30_a1_rhs"], rule=capi.RULE_MAXNORM, eps_p=1e-7, eps_r=-1.0, eps_e=1e-3,
+                          max_it=10000)
+        assert info["iterations"] == int(info_ref[0]) and info["stop_reason"] == capi.STOP_NAMES[int(info_ref[2])]
+        assert info["err_max"] == np.finfo(np.float64).max == info_ref[5]
+        assert relmax(x, x_ref) < REL
 
 
-def test_exact_error_rule(capi, oracle_mod):
-    o = oracle_for(oracle_mod, 30, 1)
-    u = o.true_solution()
-    ref = o.msg_solve(u=u, eps_p=-1.0, eps_r=-1.0, eps_e=5e-3, max_it=10000)
-    assert ref["stop_reason"] == "EXACT_ERROR"
+def test_exact_error_rule(capi, golden_ref, golden_msg):
+    """The exact-error rule firing, against a run of the unmodified reference (msg_solver.cpp:158-162)."""
+    info_ref, x_ref = golden_msg["msg_n30_a1_exact_info"], golden_msg["msg_n30_a1_exact_x"]
+    assert capi.STOP_NAMES[int(info_ref[2])] == "EXACT_ERROR"
+    b, u = golden_ref["grid_n30_a1_rhs"], golden_ref["grid_n30_a1_true"]
     for op in (0, 1):
         with plan_for(capi, 30, 1) as p:
             if op:
                 p.assemble_csr()
-            x, info = p.solve(b=o.rhs(), u=u, op=op, rule=capi.RULE_MAXNORM, eps_e=5e-3, max_it=10000)
-            assert info["stop_reason"] == "EXACT_ERROR" and abs(info["iterations"] - ref["iterations"]) <= 1
-            assert relmax(x, ref["x"]) < 1e-9
+            x, info = p.solve(b=b, u=u, op=op, rule=capi.RULE_MAXNORM, eps_e=5e-3, max_it=10000)
+            assert info["stop_reason"] == "EXACT_ERROR" and abs(info["iterations"] - int(info_ref[0])) <= 1
+            assert relmax(x, x_ref) < 1e-9
 
 
 # ---------------------------------------------------------------- CSR path
