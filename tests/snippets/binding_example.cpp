@@ -46,7 +46,7 @@ class MatrixFreeSolver {
     prm.rule = B200CG_RULE_REL_L2;
     prm.eps_rel = eps;
     prm.max_it = maxIterations;
-    prm.single_sweep = 0;  // 1: one sweep per iteration (opt-in)
+    prm.single_sweep = 0;  // the plan's default: one sweep per iteration (2: the two-sweep iteration)
     b200cg_info info;
     std::vector<double> x(system.size());
     auto tramp = [](void* u, int it, double p, double r, double e) { (*static_cast<IterationCallback*>(u))(it, p, r, e); };
@@ -58,6 +58,28 @@ class MatrixFreeSolver {
       completion_callback(info.converged != 0, info.converged ? "Converged successfully"
                                                               : "Failed to converge within maximum iterations");
     return x;
+  }
+
+  // many right-hand sides (time steps, parameter sweeps): solve() once per entry, host copies under the iterations
+  std::vector<std::vector<double>> solveBatch(const MatrixFreeSystem& system, const std::vector<std::vector<double>>& rhs) {
+    b200cg_params prm = {};
+    prm.op = B200CG_OP_MATRIX_FREE;
+    prm.rule = B200CG_RULE_REL_L2;
+    prm.eps_rel = eps;
+    prm.max_it = maxIterations;
+    std::vector<std::vector<double>> xs(rhs.size(), std::vector<double>(system.size()));
+    std::vector<const double*> bp;
+    std::vector<double*> xp;
+    for (size_t i = 0; i < rhs.size(); ++i) {
+      bp.push_back(rhs[i].data());
+      xp.push_back(xs[i].data());
+    }
+    std::vector<b200cg_info> infos(rhs.size());
+    auto done = [](void* u, int i, const b200cg_info* info) { static_cast<MatrixFreeSolver*>(u)->iterations = info->iterations + 0 * i; };
+    if (b200cg_solve_batch(system.plan_, &prm, static_cast<int>(rhs.size()), bp.data(), xp.data(), infos.data(), +done, this,
+                           nullptr))
+      throw std::runtime_error(b200cg_last_error());
+    return xs;
   }
 };
 
