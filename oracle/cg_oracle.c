@@ -142,10 +142,11 @@ void cgo_node_coords(const cgo_grid* g, double* xs, double* ys) {
   }
 }
 
-/* MatrixFreeSystem::apply, matrix_free_system.cpp:203-340. Same accumulation order per row:
- * y = 0; y += A*x[row]; y += xk*x[left]; y += xk*x[right]; y += yk*x[top]; y += yk*x[bottom];
- * a neighbour term is dropped when the neighbour is a boundary node (:221,:233,:245,:257). */
-void cgo_apply(const cgo_grid* g, const double* x, double* y) {
+/* MatrixFreeSystem::apply, matrix_free_system.cpp:203-340, node by node as the reference writes it. Same accumulation order
+ * per row: y = 0; y += A*x[row]; y += xk*x[left]; y += xk*x[right]; y += yk*x[top]; y += yk*x[bottom];
+ * a neighbour term is dropped when the neighbour is a boundary node (:221,:233,:245,:257). This form DEFINES the
+ * restatement; cgo_apply below is the same arithmetic walked row by row (tests assert bit-equality of the two). */
+void cgo_apply_nodewise(const cgo_grid* g, const double* x, double* y) {
   long N = cgo_size(g);
   for (long row = 0; row < N; ++row) {
     int xi, yi;
@@ -157,6 +158,65 @@ void cgo_apply(const cgo_grid* g, const double* x, double* y) {
     if (!is_top_boundary(g, xi, yi + 1)) acc += g->yk * x[cgo_index(g, xi, yi + 1)];
     if (!is_bottom_boundary(g, xi, yi - 1)) acc += g->yk * x[cgo_index(g, xi, yi - 1)];
     y[row] = acc;
+  }
+}
+
+/* First / last unknown column of grid row yy (empty: lo > hi) and the compact index of its first unknown. */
+static void row_span(const cgo_grid* g, int yy, int* lo, int* hi, long* base) {
+  *lo = 1;
+  *hi = 0;
+  *base = 0;
+  if (yy < 1 || yy > g->m - 1) return;
+  *lo = (g->kind != CGO_RECT && yy <= g->m / 2) ? g->n / 2 + 1 : 1;
+  *hi = g->n - 1;
+  if (*lo <= *hi) *base = cgo_index(g, *lo, yy);
+}
+
+/* The same operator walked row by row (the node-wise form spends its time in index arithmetic: a division and four
+ * index evaluations per node). Per node the same products are added in the same order - diag, left, right, top, bottom -
+ * and a neighbour contributes exactly when it is an unknown, which on every grid cgo_grid_init accepts is the complement
+ * of "is a boundary node" among the four neighbours of an unknown. Bit-identical to cgo_apply_nodewise (tests). */
+void cgo_apply(const cgo_grid* g, const double* x, double* y) {
+  const double A = g->A, xk = g->xk, yk = g->yk;
+  for (int yi = 1; yi <= g->m - 1; ++yi) {
+    int lo, hi, tlo, thi, blo, bhi;
+    long base, tbase, bbase;
+    row_span(g, yi, &lo, &hi, &base);
+    if (lo > hi) continue;
+    row_span(g, yi + 1, &tlo, &thi, &tbase);
+    row_span(g, yi - 1, &blo, &bhi, &bbase);
+    const double* xr = x + base - lo;    /* xr[xi] = x(xi, yi) */
+    const double* xt = x + tbase - tlo;  /* xt[xi] = x(xi, yi + 1) where tlo <= xi <= thi */
+    const double* xb = x + bbase - blo;
+    double* yr = y + base - lo;
+    /* columns whose four neighbours are all unknowns */
+    int ilo = lo + 1, ihi = hi - 1;
+    if (tlo > ilo) ilo = tlo;
+    if (blo > ilo) ilo = blo;
+    if (thi < ihi) ihi = thi;
+    if (bhi < ihi) ihi = bhi;
+    if (tlo > thi || blo > bhi) ihi = ilo - 1;  /* no row above / below: no such column */
+    for (int xi = lo; xi <= hi; ++xi) {
+      if (xi == ilo && ilo <= ihi) {
+        for (; xi <= ihi; ++xi) {
+          double acc = 0.0;
+          acc += A * xr[xi];
+          acc += xk * xr[xi - 1];
+          acc += xk * xr[xi + 1];
+          acc += yk * xt[xi];
+          acc += yk * xb[xi];
+          yr[xi] = acc;
+        }
+        if (xi > hi) break;
+      }
+      double acc = 0.0;
+      acc += A * xr[xi];
+      if (xi - 1 >= lo) acc += xk * xr[xi - 1];
+      if (xi + 1 <= hi) acc += xk * xr[xi + 1];
+      if (tlo <= thi && xi >= tlo && xi <= thi) acc += yk * xt[xi];
+      if (blo <= bhi && xi >= blo && xi <= bhi) acc += yk * xb[xi];
+      yr[xi] = acc;
+    }
   }
 }
 

@@ -38,7 +38,8 @@ void cgo_node(const cgo_grid* g, long idx, int* x, int* y);
 void cgo_rhs(const cgo_grid* g, double* b);                      /* N */
 void cgo_true_solution(const cgo_grid* g, double* u);            /* N */
 void cgo_node_coords(const cgo_grid* g, double* xs, double* ys); /* N each */
-void cgo_apply(const cgo_grid* g, const double* x, double* y);   /* y = A x */
+void cgo_apply(const cgo_grid* g, const double* x, double* y);   /* y = A x (row-wise walk of the form below) */
+void cgo_apply_nodewise(const cgo_grid* g, const double* x, double* y); /* the reference's node-by-node form */
 
 typedef struct {
   int iterations;

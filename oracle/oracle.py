@@ -110,6 +110,13 @@ class Oracle:
         self.L.cgo_apply(C.byref(self.g), _opt(x), _opt(y))
         return y
 
+    def apply_nodewise(self, x):
+        """The same operator in the reference's node-by-node form (the definition cgo_apply is checked against)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.N)
+        self.L.cgo_apply_nodewise(C.byref(self.g), _opt(x), _opt(y))
+        return y
+
     def mf_solve(self, b=None, eps=1e-6, max_it=10000, with_hist=False, snapshots=False, accurate_dots=False):
         """accurate_dots=True: diagnostic long-double summation instead of the reference's sequential fp64."""
         self.L.cgo_set_dot_mode(1 if accurate_dots else 0)

@@ -177,6 +177,20 @@ def test_port_equals_the_compiled_reference_at_config2_size(oracle_mod):
     assert rs["iterations"] == ps["iterations"] == 5 and np.array_equal(rs["x"], ps["x"])
 
 
+@pytest.mark.parametrize("m,n,kind", [(4, 4, 0), (6, 6, 0), (30, 30, 0), (128, 128, 0), (2, 2, 1), (2, 5, 1), (7, 9, 1),
+                                      (37, 1200, 1), (4, 4, 3), (5, 4, 3), (4, 5, 3), (9, 12, 3), (12, 9, 3), (33, 20, 3),
+                                      (481, 333, 3)])
+def test_rowwise_apply_is_the_nodewise_apply(oracle_mod, m, n, kind):
+    """cgo_apply walks the operator row by row for speed; cgo_apply_nodewise is the reference's node-by-node form
+    (matrix_free_system.cpp:203-340: boundary predicates and index formulas per neighbour). Same products in the same order:
+    bit-identical on every domain kind, square or not, even or odd."""
+    o = oracle_mod.Oracle(m, n, 0.0, 1.0, -1.0, 0.5, kind) if kind else oracle_mod.Oracle(m, n, 0.0, 1.0, 0.0, 1.0)
+    rng = np.random.default_rng(m * 1000 + n)
+    for _ in range(2):
+        v = rng.standard_normal(o.N)
+        assert np.array_equal(o.apply(v), o.apply_nodewise(v))
+
+
 def test_reference_rejects_what_oracle_rejects(oracle_mod):
     """The reference numbering is only self-consistent for even n == m; the oracle refuses the rest."""
     for n, m in [(8, 6), (7, 7), (2, 2)]:
